@@ -1,0 +1,185 @@
+// device_common.cuh -- data layout and warp-level building blocks shared by the GRank / MC kernels.
+//
+// HBM layout (DESIGN.md "Data layout"):
+//   * Non-sink nodes live at "storage positions" p = 0..M-1 (colour-major, then class, then out-degree
+//     descending). Sinks own no storage: their basket is the constant {v: 1-d} (GRank) / {v: 1} (MC).
+//   * row_off[M+1] (int64) / col[E'] (uint32): CSR in storage order. A col word is
+//        sink successor      : 0x80000000 | dense id of the sink
+//        non-sink successor  : storage position | colour << 30
+//   * label[M]: dense (external) id of the node at position p. Basket entries carry dense ids, so the
+//     canonical tie-break (score desc, dense id asc) is independent of the storage order.
+//   * baskets: two buffers of M slots; a slot is Lp = roundup4(L) entries stored as
+//        int32 ids[Lp] | double scoreA[Lp/2] | double scoreB[Lp/2]
+//     where entry e = 4g + r keeps its score in scoreA[2g + r] (r < 2) or scoreB[2g + r - 2] (r >= 2), so
+//     lane g fetches four entries with three fully coalesced 16-byte loads. Unused entries have id -1.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pprb200 {
+
+constexpr int KEY_EMPTY = -1;
+constexpr uint32_t COL_SINK = 0x80000000u;
+constexpr uint32_t COL_COLOUR_SHIFT = 30;
+constexpr uint32_t COL_POS_MASK = 0x3fffffffu;
+constexpr unsigned FULL = 0xffffffffu;
+
+constexpr double NORM_SCALE = 0x1p61;   // norm1 fixed point (order-free sum, oracle/ppr_oracle.c)
+constexpr double NORM_INV = 0x1p-61;
+constexpr double GRANK_HUB_SCALE = 0x1p62, GRANK_HUB_INV = 0x1p-62;
+constexpr double MC_HUB_SCALE = 0x1p59, MC_HUB_INV = 0x1p-59;
+
+enum : int { MODE_GRANK = 0, MODE_MC = 1 };
+
+// device-resident control block of one run (one per session)
+struct RunState {
+  int slot[2];               // buffer holding the current baskets of colour c
+  int active;                // 1 while iterating; cleared by the convergence test (grank.h:92)
+  int iter;                  // iterations executed so far
+  long long m_prev, m_last;  // maxDiff of the two most recent iterations, 2^-61 fixed point
+  long long cur_max;         // running max of the iteration in flight
+  unsigned int work[8];      // work-fetch counters, one per kernel stage
+  unsigned int qcount[4];    // overflow queue lengths (nodes that need a larger table)
+  unsigned long long node_iters, edge_reads, merged, cands, truncs, ties, abytes, requeues;
+  unsigned long long walk_steps, walks;
+  unsigned int ws_next;      // bump allocator for the global-table workspace
+  unsigned int pad;
+};
+
+struct GraphDev {
+  const long long* row_off;  // [M+1]
+  const uint32_t* col;       // [E']
+  const int* label;          // [M]
+};
+
+__host__ __device__ inline int roundup4(int x) { return (x + 3) & ~3; }
+__host__ __device__ inline size_t slot_bytes(int Lp) { return (size_t)Lp * 12; }
+
+__device__ __forceinline__ int score_index(int e, int Lp) {
+  const int g = e >> 2, r = e & 3;
+  return (r < 2) ? (2 * g + r) : ((Lp >> 1) + 2 * g + r - 2);
+}
+
+__device__ __forceinline__ uint32_t hash_key(int k) {
+  uint32_t x = (uint32_t)k * 0x9E3779B1u;
+  return x ^ (x >> 15);
+}
+
+__device__ __forceinline__ long long fix_norm(double x) { return __double2ll_rn(x * NORM_SCALE); }
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_ull(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_max_ull(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(FULL, v, o); v = t > v ? t : v; }
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_min_ull(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(FULL, v, o); v = t < v ? t : v; }
+  return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-level radix select (keepTop, pprInternal.h:109-137, with the canonical tie-break).
+// Finds the k-th largest of the 64-bit keys key(i), i in [0,n) with pred(i); 8-bit digits from the highest
+// differing bit down; stops as soon as the boundary bucket is taken whole.
+// Returns the threshold t: every in-play key > t is selected; if !tie all keys == (t's known prefix) bucket
+// are selected too (selected <=> key >= t); if tie, `krem` of the keys == t must still be chosen.
+// hist: 256 uint32 of shared memory private to the warp.
+// ------------------------------------------------------------------------------------------------
+template <typename KeyFn, typename PredFn>
+__device__ unsigned long long warp_radix_select(int n, int k, KeyFn key, PredFn pred, unsigned int* hist,
+                                                bool* tie, int* krem) {
+  const int lane = lane_id();
+  unsigned long long lo = ~0ull, hi = 0ull;
+  for (int i = lane; i < n; i += 32)
+    if (pred(i)) { const unsigned long long b = key(i); lo = b < lo ? b : lo; hi = b > hi ? b : hi; }
+  lo = warp_min_ull(lo);
+  hi = warp_max_ull(hi);
+  *tie = false;
+  *krem = 0;
+  if (lo == hi) {  // every in-play key identical
+    int cnt = 0;
+    for (int i = lane; i < n; i += 32) cnt += pred(i) ? 1 : 0;
+    cnt = warp_sum_int(cnt);
+    if (cnt > k) { *tie = true; *krem = k; }
+    return lo;
+  }
+  const int top = 63 - __clzll((long long)(lo ^ hi));
+  unsigned long long known = (top == 63) ? 0ull : ~((2ull << top) - 1ull);
+  unsigned long long prefix = hi & known;
+  int shift = top - 7 > 0 ? top - 7 : 0;
+  for (;;) {
+    for (int i = lane; i < 256; i += 32) hist[i] = 0;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32)
+      if (pred(i)) {
+        const unsigned long long b = key(i);
+        if ((b & known) == prefix) atomicAdd(&hist[(unsigned)(b >> shift) & 0xffu], 1u);
+      }
+    __syncwarp();
+    // lane owns bins [8*lane, 8*lane+8); walk from the top bin down
+    unsigned int mine[8];
+    unsigned int local = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { mine[j] = hist[lane * 8 + j]; local += mine[j]; }
+    // above = in-play keys in bins of higher lanes
+    unsigned int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_down_sync(FULL, incl, o);
+      if (lane + o < 32) incl += t;
+    }
+    const unsigned int above = incl - local;
+    const bool here = above < (unsigned)k && incl >= (unsigned)k;
+    const unsigned ball = __ballot_sync(FULL, here);
+    const int owner = __ffs(ball) - 1;  // exactly one lane
+    int digit = 0;
+    unsigned int cnt_above = 0, cnt_d = 0;
+    if (lane == owner) {
+      unsigned int run = above;
+#pragma unroll
+      for (int j = 7; j >= 0; j--) {
+        if (run < (unsigned)k && run + mine[j] >= (unsigned)k) { digit = lane * 8 + j; cnt_above = run; cnt_d = mine[j]; }
+        run += mine[j];
+      }
+    }
+    digit = __shfl_sync(FULL, digit, owner);
+    cnt_above = __shfl_sync(FULL, cnt_above, owner);
+    cnt_d = __shfl_sync(FULL, cnt_d, owner);
+    k -= (int)cnt_above;
+    prefix |= (unsigned long long)digit << shift;
+    known |= 0xffull << shift;
+    __syncwarp();
+    if ((int)cnt_d == k) return prefix;  // whole bucket selected; unknown low bits of the threshold are 0
+    if (shift == 0) { *tie = true; *krem = k; return prefix; }
+    shift = shift - 8 > 0 ? shift - 8 : 0;
+  }
+}
+
+struct Threshold {
+  unsigned long long bits;  // selected <=> score bits > bits, or == bits and id <= id_max
+  int id_max;
+};
+
+__device__ __forceinline__ bool is_selected(const Threshold& t, unsigned long long bits, int id) {
+  return bits > t.bits || (bits == t.bits && id <= t.id_max);
+}
+
+}  // namespace pprb200

@@ -1,0 +1,674 @@
+// ppr_b200.cu -- session management, kernel orchestration and the C-ABI of libppr_b200.so (include/pprb200.h).
+//
+// One GRank run (include/grank.h:42-150) is enqueued as
+//   init cascade (both colours)  ->  [ merge cascade(colour it&1) -> iter_end ] x iterations  ->  final top-K
+// with no host synchronisation in between: the convergence test of grank.h:92 runs on the device
+// (iter_end clears RunState::active, later launches return immediately).
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <vector>
+
+#include "merge_seq.cuh"
+#include "ppr_internal.h"
+
+namespace pprb200 {
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return fail(PPRB200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ------------------------------------------------------------------------------------------------
+// small control kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void state_reset_kernel(RunState* st) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    memset(st, 0, sizeof(RunState));
+    st->active = 1;
+    st->m_prev = -1;
+    st->m_last = -1;
+  }
+}
+
+// end of an init / combine phase: clear cascade counters (and optionally the work statistics)
+__global__ void phase_end_kernel(RunState* st, int clear_stats, int flip_both) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    for (int i = 0; i < 8; i++) st->work[i] = 0;
+    for (int i = 0; i < 4; i++) st->qcount[i] = 0;
+    if (clear_stats) {
+      st->node_iters = st->edge_reads = st->merged = st->cands = st->abytes = st->requeues = 0;
+    }
+    if (flip_both) { st->slot[0] ^= 1; st->slot[1] ^= 1; st->iter++; }
+  }
+}
+
+// end of GRank iteration `it` (0-based) on `colour`: grank.h:129-140 + the loop test of :92
+__global__ void iter_end_kernel(RunState* st, int colour, double tolerance) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    for (int i = 0; i < 8; i++) st->work[i] = 0;
+    for (int i = 0; i < 4; i++) st->qcount[i] = 0;
+    if (!st->active) return;
+    st->slot[colour] ^= 1;
+    st->iter++;
+    st->m_prev = st->m_last;
+    st->m_last = st->cur_max;
+    st->cur_max = 0;
+    // maxDiff = {tolerance, tolerance} initially (grank.h:90): the test can only fail once both slots hold
+    // measured values, i.e. from the second executed iteration on.
+    if (st->iter >= 2) {
+      const long long m = st->m_prev > st->m_last ? st->m_prev : st->m_last;
+      if (!((double)m * NORM_INV >= tolerance)) st->active = 0;
+    } else {
+      const double m1 = (double)st->m_last * NORM_INV;
+      const double mx = m1 > tolerance ? m1 : tolerance;
+      if (!(mx >= tolerance)) st->active = 0;
+    }
+  }
+}
+
+// final keepTop(K) (grank.h:143-147, mccompletepathv2.h:252-256): one warp per dense id; output sorted
+// (score desc, id asc) by rank counting over the <= L basket entries.
+__global__ void final_topk_kernel(const int* __restrict__ pos_of, const unsigned char* __restrict__ colour,
+                                  unsigned char* buf0, unsigned char* buf1, const RunState* st, int n, int Lp, int K,
+                                  double sink_score, int* __restrict__ out_ids, double* __restrict__ out_scores,
+                                  unsigned int* __restrict__ out_cnt, unsigned long long* trunc_ties) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = lane_id();
+  const int w = threadIdx.x >> 5;
+  const int warps = blockDim.x >> 5;
+  double* s_sc = reinterpret_cast<double*>(smem) + (size_t)w * Lp;
+  int* s_id = reinterpret_cast<int*>(smem + (size_t)warps * Lp * 8) + (size_t)w * Lp;
+  unsigned long long truncs = 0, ties = 0;
+  for (int v = blockIdx.x * warps + w; v < n; v += gridDim.x * warps) {
+    int* oi = out_ids + (size_t)v * K;
+    double* os = out_scores + (size_t)v * K;
+    const int p = pos_of[v];
+    if (p < 0) {  // sink
+      for (int i = lane; i < K; i += 32) { oi[i] = i == 0 ? v : KEY_EMPTY; os[i] = i == 0 ? sink_score : 0.0; }
+      if (lane == 0) out_cnt[v] = 1;
+      continue;
+    }
+    const unsigned char* slot = (st->slot[colour[v]] ? buf1 : buf0) + (size_t)p * slot_bytes(Lp);
+    const int* ids = reinterpret_cast<const int*>(slot);
+    const double* sc = reinterpret_cast<const double*>(slot + (size_t)Lp * 4);
+    int cnt = 0;
+    for (int e = lane; e < Lp; e += 32) {
+      const int id = ids[e];
+      s_id[e] = id;
+      s_sc[e] = id >= 0 ? sc[score_index(e, Lp)] : 0.0;
+      cnt += id >= 0;
+    }
+    cnt = warp_sum_int(cnt);
+    __syncwarp();
+    const int kept = cnt < K ? cnt : K;
+    bool tie = false;
+    for (int e = lane; e < cnt; e += 32) {
+      const double x = s_sc[e];
+      const int id = s_id[e];
+      int rank = 0;
+      for (int j = 0; j < cnt; j++) {
+        const double y = s_sc[j];
+        rank += (y > x) || (y == x && s_id[j] < id);
+      }
+      if (rank < K) { oi[rank] = id; os[rank] = x; }
+      if (rank == K - 1 && cnt > K) {
+        // boundary tie <=> some other entry with the same score ranks K
+        for (int j = 0; j < cnt; j++) tie |= (s_sc[j] == x && s_id[j] > id);
+      }
+    }
+    for (int i = kept + lane; i < K; i += 32) { oi[i] = KEY_EMPTY; os[i] = 0.0; }
+    if (lane == 0) out_cnt[v] = (unsigned int)kept;
+    tie = __any_sync(FULL, tie);
+    if (cnt > K) { truncs += (lane == 0); ties += (lane == 0 && tie); }
+    __syncwarp();
+  }
+  if (lane == 0 && truncs) { atomicAdd(&trunc_ties[0], truncs); atomicAdd(&trunc_ties[1], ties); }
+}
+
+}  // namespace pprb200
+
+using namespace pprb200;
+
+// ------------------------------------------------------------------------------------------------
+// session
+// ------------------------------------------------------------------------------------------------
+struct StageCfg {
+  int cap;      // 0 = global workspace
+  int warps;    // warps per CTA
+  int grid;     // CTAs
+  size_t smem;  // dynamic shared memory per CTA
+  int limit;
+};
+
+struct pprb200_session {
+  int32_t n = 0;
+  int32_t M = 0;  // non-sink nodes
+  int64_t E = 0;
+  uint32_t max_L = 0, hub_threshold = 0;
+  int rank = 0, world = 1;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  // storage ranges [colour]: all non-sink nodes of that colour (seq class first, then hub class)
+  int range_begin[2] = {0, 0}, range_end[2] = {0, 0};
+  int32_t colour_count[2] = {0, 0};  // all nodes (sinks included) per colour
+  int32_t max_deg = 0;
+  // device
+  long long* d_row_off = nullptr;
+  uint32_t* d_col = nullptr;
+  int* d_label = nullptr;
+  int* d_pos_of = nullptr;
+  unsigned char* d_colour = nullptr;
+  unsigned char* d_buf[2] = {nullptr, nullptr};
+  size_t buf_bytes = 0;
+  unsigned int* d_queue[3] = {nullptr, nullptr, nullptr};
+  int* d_ncand = nullptr;
+  RunState* d_state = nullptr;
+  unsigned long long* d_final_stats = nullptr;
+  unsigned char* d_ws = nullptr;
+  size_t ws_bytes = 0;
+  int* d_out_ids = nullptr;
+  double* d_out_scores = nullptr;
+  unsigned int* d_out_cnt = nullptr;
+  size_t out_capacity = 0;  // n*K entries allocated
+  // last run
+  int last_mode = -1;
+  uint32_t last_K = 0, last_L = 0, last_iterations = 0;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  std::vector<cudaEvent_t> ev_merge;  // pairs (begin,end) per iteration
+  uint32_t merge_launches = 0;
+  double prep_ms = 0, h2d_ms = 0;
+};
+
+static int device_ok() {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
+    cudaGetLastError();
+    return fail(PPRB200_ERR_CUDA, "no CUDA device available (libppr_b200 has no CPU fallback)");
+  }
+  cudaDeviceProp pr;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (cudaGetDeviceProperties(&pr, dev) != cudaSuccess) return fail(PPRB200_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (pr.major != 10) return fail(PPRB200_ERR_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only", pr.name, pr.major, pr.minor);
+  return PPRB200_OK;
+}
+
+template <typename T>
+static int dev_alloc(T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  if (e != cudaSuccess) return fail(PPRB200_ERR_ALLOC, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+  return PPRB200_OK;
+}
+
+static void session_free(pprb200_session* s) {
+  if (!s) return;
+  cudaFree(s->d_row_off); cudaFree(s->d_col); cudaFree(s->d_label); cudaFree(s->d_pos_of); cudaFree(s->d_colour);
+  cudaFree(s->d_buf[0]); cudaFree(s->d_buf[1]);
+  for (int i = 0; i < 3; i++) cudaFree(s->d_queue[i]);
+  cudaFree(s->d_ncand); cudaFree(s->d_state); cudaFree(s->d_final_stats); cudaFree(s->d_ws);
+  cudaFree(s->d_out_ids); cudaFree(s->d_out_scores); cudaFree(s->d_out_cnt);
+  if (s->ev_begin) cudaEventDestroy(s->ev_begin);
+  if (s->ev_end) cudaEventDestroy(s->ev_end);
+  for (auto e : s->ev_merge) cudaEventDestroy(e);
+  delete s;
+}
+
+static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour_in,
+                               uint32_t max_L, uint32_t hub_threshold, int32_t rank, int32_t world, void* stream,
+                               pprb200_session** out) {
+  if (!out) return fail(PPRB200_ERR_PARAM, "out is NULL");
+  *out = nullptr;
+  if (max_L == 0) return fail(PPRB200_ERR_PARAM, "L must be positive");
+  if (world != 1 || rank != 0) return fail(PPRB200_ERR_PARAM, "multi-rank sessions are not available in this build (world=%d)", world);
+  int rc = validate_csr(row_ptr, col, n);
+  if (rc) return rc;
+  rc = device_ok();
+  if (rc) return rc;
+
+  const double t0 = now_ms();
+  pprb200_session* s = new pprb200_session();
+  s->n = n;
+  s->max_L = max_L;
+  s->hub_threshold = hub_threshold == 0 ? PPRB200_DEFAULT_HUB_THRESHOLD : hub_threshold;
+  s->rank = rank;
+  s->world = world;
+  s->stream = (cudaStream_t)stream;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
+
+  std::vector<uint8_t> colour((size_t)n);
+  if (colour_in) std::memcpy(colour.data(), colour_in, (size_t)n);
+  else if ((rc = find_partitions(row_ptr, col, n, colour.data()))) { delete s; return rc; }
+  for (int32_t v = 0; v < n; v++) {
+    if (colour[v] > 1) { delete s; return fail(PPRB200_ERR_PARAM, "colour[%d] = %d is not 0/1", v, colour[v]); }
+    s->colour_count[colour[v]]++;
+  }
+
+  // storage order: colour-major, out-degree descending (ties by dense id) -- big nodes first for load balance
+  std::vector<int32_t> order;
+  order.reserve((size_t)n);
+  for (int c = 0; c < 2; c++) {
+    s->range_begin[c] = (int)order.size();
+    const size_t b = order.size();
+    for (int32_t v = 0; v < n; v++)
+      if (colour[v] == c && row_ptr[v + 1] > row_ptr[v]) order.push_back(v);
+    std::stable_sort(order.begin() + (long)b, order.end(), [&](int32_t x, int32_t y) {
+      return (row_ptr[x + 1] - row_ptr[x]) > (row_ptr[y + 1] - row_ptr[y]);
+    });
+    s->range_end[c] = (int)order.size();
+  }
+  const int32_t M = (int32_t)order.size();
+  s->M = M;
+  std::vector<int32_t> pos_of((size_t)n, -1);
+  for (int32_t p = 0; p < M; p++) pos_of[order[p]] = p;
+  std::vector<long long> row_off((size_t)M + 1, 0);
+  for (int32_t p = 0; p < M; p++) {
+    const int64_t d = row_ptr[order[p] + 1] - row_ptr[order[p]];
+    row_off[(size_t)p + 1] = row_off[p] + d;
+    if (d > s->max_deg) s->max_deg = (int32_t)std::min<int64_t>(d, INT32_MAX);
+  }
+  const int64_t E = row_off[M];
+  s->E = E;
+  std::vector<uint32_t> enc((size_t)std::max<int64_t>(E, 1));
+  for (int32_t p = 0; p < M; p++) {
+    const int32_t v = order[p];
+    long long o = row_off[p];
+    for (int64_t i = row_ptr[v]; i < row_ptr[v + 1]; i++) {
+      const int32_t su = col[i];
+      enc[(size_t)o++] = pos_of[su] < 0 ? (COL_SINK | (uint32_t)su)
+                                         : ((uint32_t)pos_of[su] | ((uint32_t)colour[su] << COL_COLOUR_SHIFT));
+    }
+  }
+  s->prep_ms = now_ms() - t0;
+
+  const double t1 = now_ms();
+  const int Lp = roundup4((int)max_L);
+  s->buf_bytes = (size_t)std::max(M, 1) * slot_bytes(Lp);
+  if ((rc = dev_alloc(&s->d_row_off, (size_t)M + 1)) || (rc = dev_alloc(&s->d_col, (size_t)E)) ||
+      (rc = dev_alloc(&s->d_label, (size_t)M)) || (rc = dev_alloc(&s->d_pos_of, (size_t)n)) ||
+      (rc = dev_alloc(&s->d_colour, (size_t)n)) || (rc = dev_alloc(&s->d_buf[0], s->buf_bytes)) ||
+      (rc = dev_alloc(&s->d_buf[1], s->buf_bytes)) || (rc = dev_alloc(&s->d_queue[0], (size_t)M)) ||
+      (rc = dev_alloc(&s->d_queue[1], (size_t)M)) || (rc = dev_alloc(&s->d_queue[2], (size_t)M)) ||
+      (rc = dev_alloc(&s->d_ncand, (size_t)M)) || (rc = dev_alloc(&s->d_state, 1)) ||
+      (rc = dev_alloc(&s->d_final_stats, 2))) {
+    session_free(s);
+    return rc;
+  }
+  cudaStream_t st = s->stream;
+#define UP(dst, src, bytes)                                                                          \
+  do {                                                                                               \
+    cudaError_t _e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);                   \
+    if (_e != cudaSuccess) { session_free(s); return fail(PPRB200_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(_e)); } \
+  } while (0)
+  UP(s->d_row_off, row_off.data(), ((size_t)M + 1) * sizeof(long long));
+  if (E) UP(s->d_col, enc.data(), (size_t)E * sizeof(uint32_t));
+  if (M) UP(s->d_label, order.data(), (size_t)M * sizeof(int));
+  if (n) UP(s->d_pos_of, pos_of.data(), (size_t)n * sizeof(int));
+  if (n) UP(s->d_colour, colour.data(), (size_t)n);
+#undef UP
+  cudaError_t e = cudaStreamSynchronize(st);  // host vectors go out of scope
+  if (e != cudaSuccess) { session_free(s); return fail(PPRB200_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e)); }
+  cudaMemsetAsync(s->d_ncand, 0, (size_t)std::max(M, 1) * sizeof(int), st);
+  cudaEventCreate(&s->ev_begin);
+  cudaEventCreate(&s->ev_end);
+  s->h2d_ms = now_ms() - t1;
+  *out = s;
+  return PPRB200_OK;
+}
+
+// ---- stage configuration -----------------------------------------------------------------------
+static int stage_limit(int cap, int Lp) {
+  const int guard = std::max(Lp, 32) + 1;
+  return std::min(cap * 3 / 4, cap - guard);
+}
+
+static unsigned int next_pow2(unsigned long long x) {
+  unsigned long long p = 1;
+  while (p < x) p <<= 1;
+  return (unsigned int)std::min<unsigned long long>(p, 1ull << 31);
+}
+
+template <int CAP, int WARPS, typename IdxT>
+static cudaError_t launch_stage(const pprb200_session* s, const MergeParams& P, int grid, size_t smem, unsigned char* ws,
+                                unsigned int ws_cap, int ws_identity) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(merge_seq_kernel<CAP, WARPS, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  merge_seq_kernel<CAP, WARPS, IdxT><<<grid, WARPS * 32, smem, s->stream>>>(P, ws, ws_cap, ws_identity);
+  return cudaGetLastError();
+}
+
+// Enqueue the table-size cascade for one colour (or, MC, for everything): 1024 -> 4096 -> 16384 -> global.
+static int enqueue_cascade(pprb200_session* s, MergeParams P, int range_begin, int range_end, int L) {
+  const int Lp = roundup4(L);
+  P.Lp = Lp;
+  P.L = L;
+  const int caps[3] = {1024, 4096, 16384};
+  const int warps[3] = {14, 3, 1};
+  bool have_source = false;  // false: next stage reads the range; true: reads queue `qsrc`
+  int qsrc = -1;
+  int work_idx = 0;
+  for (int i = 0; i < 3; i++) {
+    const int limit = stage_limit(caps[i], Lp);
+    if (limit < 8) continue;
+    MergeParams Q = P;
+    Q.limit = limit;
+    Q.work_idx = work_idx++;
+    if (!have_source) { Q.range_begin = range_begin; Q.range_end = range_end; Q.queue_in = nullptr; Q.queue_in_idx = -1; }
+    else { Q.queue_in = s->d_queue[qsrc]; Q.queue_in_idx = qsrc; }
+    const int qdst = qsrc + 1;
+    Q.queue_out = s->d_queue[qdst];
+    Q.queue_out_idx = qdst;
+    const size_t smem = (size_t)warps[i] * ((size_t)caps[i] * 14 + 1040);
+    cudaError_t e;
+    if (i == 0) e = launch_stage<1024, 14, unsigned short>(s, Q, s->sm_count, smem, nullptr, 0, 0);
+    else if (i == 1) e = launch_stage<4096, 3, unsigned short>(s, Q, s->sm_count, smem, nullptr, 0, 0);
+    else e = launch_stage<16384, 1, unsigned short>(s, Q, s->sm_count, smem, nullptr, 0, 0);
+    if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge stage %d launch failed: %s", i, cudaGetErrorString(e));
+    have_source = true;
+    qsrc = qdst;
+  }
+  // final stage: table in the global workspace, sized for the worst case of this run -> cannot overflow
+  {
+    MergeParams Q = P;
+    Q.limit = 0x7fffffff;
+    Q.work_idx = work_idx++;
+    if (!have_source) { Q.range_begin = range_begin; Q.range_end = range_end; Q.queue_in = nullptr; Q.queue_in_idx = -1; }
+    else { Q.queue_in = s->d_queue[qsrc]; Q.queue_in_idx = qsrc; }
+    Q.queue_out = nullptr;
+    Q.queue_out_idx = 0;
+    const unsigned long long bound = std::min<unsigned long long>((unsigned long long)s->max_deg * (unsigned long long)Lp + 2ull + 32ull,
+                                                                  (unsigned long long)s->n + 1ull);
+    unsigned int cap;
+    int identity;
+    if ((unsigned long long)s->n <= 2 * bound) { cap = next_pow2((unsigned long long)std::max(s->n, 64)); identity = 1; }
+    else { cap = next_pow2(2 * bound); identity = 0; }
+    const size_t region = (size_t)cap * 16;  // vals 8 + keys 4 + list 4
+    const size_t budget = (size_t)8 << 30;
+    int gw = (int)std::max<size_t>(1, std::min<size_t>((size_t)s->sm_count * 8, budget / region));
+    const int warps_g = 4;
+    int grid = std::max(1, gw / warps_g);
+    const size_t need = (size_t)grid * warps_g * region;
+    if (need > s->ws_bytes) {
+      cudaFree(s->d_ws);
+      s->d_ws = nullptr;
+      s->ws_bytes = 0;
+      int rc = dev_alloc(&s->d_ws, need);
+      if (rc) return rc;
+      s->ws_bytes = need;
+    }
+    cudaError_t e = launch_stage<0, 4, unsigned int>(s, Q, grid, (size_t)warps_g * 1040, s->d_ws, cap, identity);
+    if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "global merge stage launch failed: %s", cudaGetErrorString(e));
+  }
+  return PPRB200_OK;
+}
+
+static int ensure_outputs(pprb200_session* s, uint32_t K) {
+  const size_t need = (size_t)std::max(s->n, 1) * K;
+  if (need > s->out_capacity) {
+    cudaFree(s->d_out_ids); cudaFree(s->d_out_scores);
+    s->d_out_ids = nullptr; s->d_out_scores = nullptr; s->out_capacity = 0;
+    int rc;
+    if ((rc = dev_alloc(&s->d_out_ids, need)) || (rc = dev_alloc(&s->d_out_scores, need))) return rc;
+    s->out_capacity = need;
+  }
+  if (!s->d_out_cnt) { int rc = dev_alloc(&s->d_out_cnt, (size_t)std::max(s->n, 1)); if (rc) return rc; }
+  return PPRB200_OK;
+}
+
+static int enqueue_final(pprb200_session* s, int L, uint32_t K, double sink_score) {
+  const int Lp = roundup4(L);
+  const int warps = 8;
+  const size_t smem = (size_t)warps * Lp * 12;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(final_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "final_topk smem %zu: %s", smem, cudaGetErrorString(e));
+    configured = smem;
+  }
+  cudaMemsetAsync(s->d_final_stats, 0, 2 * sizeof(unsigned long long), s->stream);
+  const int grid = std::max(1, std::min((s->n + warps - 1) / warps, s->sm_count * 8));
+  final_topk_kernel<<<grid, warps * 32, smem, s->stream>>>(s->d_pos_of, s->d_colour, s->d_buf[0], s->d_buf[1], s->d_state,
+                                                           s->n, Lp, (int)K, sink_score, s->d_out_ids, s->d_out_scores,
+                                                           s->d_out_cnt, s->d_final_stats);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "final_topk launch failed: %s", cudaGetErrorString(e));
+  return PPRB200_OK;
+}
+
+static int check_params(uint32_t K, uint32_t L, uint32_t iterations, double damping) {
+  if (K == 0) return fail(PPRB200_ERR_PARAM, "K must be positive");
+  if (L == 0) return fail(PPRB200_ERR_PARAM, "L must be positive");
+  if (K > L) return fail(PPRB200_ERR_PARAM, "K must be <= L");
+  if (iterations == 0) return fail(PPRB200_ERR_PARAM, "iterations must be positive");
+  if (!(damping >= 0 && damping <= 1)) return fail(PPRB200_ERR_PARAM, "damping must be [0,1]");
+  return PPRB200_OK;
+}
+
+static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t iterations, double damping,
+                              double tolerance) {
+  int rc = check_params(K, L, iterations, damping);
+  if (rc) return rc;
+  if (L > s->max_L) return fail(PPRB200_ERR_PARAM, "L=%u exceeds the session's max_L=%u", L, s->max_L);
+  if ((size_t)roundup4((int)L) * 12 * 8 > 200 * 1024) return fail(PPRB200_ERR_PARAM, "L=%u too large for the final top-K kernel", L);
+  if ((rc = ensure_outputs(s, K))) return rc;
+  s->last_mode = MODE_GRANK;
+  s->last_K = K; s->last_L = L; s->last_iterations = iterations;
+  while (s->ev_merge.size() < 2 * (size_t)iterations) { cudaEvent_t e; cudaEventCreate(&e); s->ev_merge.push_back(e); }
+  s->merge_launches = 0;
+
+  cudaStream_t st = s->stream;
+  cudaEventRecord(s->ev_begin, st);
+  state_reset_kernel<<<1, 1, 0, st>>>(s->d_state);
+  MergeParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.g.row_off = s->d_row_off; P.g.col = s->d_col; P.g.label = s->d_label;
+  P.buf[0] = s->d_buf[0]; P.buf[1] = s->d_buf[1];
+  P.st = s->d_state;
+  P.mode = MODE_GRANK;
+  P.damping = damping;
+  P.self_grank = 1.0 - damping;
+  P.ncand = s->d_ncand;
+  if (s->M > 0) {
+    // init (grank.h:64-83)
+    cudaMemsetAsync(s->d_ncand, 0, (size_t)s->M * sizeof(int), st);
+    for (int c = 0; c < 2; c++) {
+      if (s->range_end[c] == s->range_begin[c]) continue;
+      MergeParams Q = P;
+      Q.init_mode = 1; Q.do_norm = 0; Q.colour = c;
+      if ((rc = enqueue_cascade(s, Q, s->range_begin[c], s->range_end[c], (int)L))) return rc;
+      phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 1, 0);
+    }
+  }
+  for (uint32_t it = 0; it < iterations; it++) {
+    const int c = (int)(it & 1);  // partitions.first on even iterations (grank.h:96,129)
+    cudaEventRecord(s->ev_merge[2 * it], st);
+    if (s->range_end[c] > s->range_begin[c]) {
+      MergeParams Q = P;
+      Q.init_mode = 0; Q.do_norm = 1; Q.colour = c;
+      if ((rc = enqueue_cascade(s, Q, s->range_begin[c], s->range_end[c], (int)L))) return rc;
+    }
+    cudaEventRecord(s->ev_merge[2 * it + 1], st);
+    iter_end_kernel<<<1, 1, 0, st>>>(s->d_state, c, tolerance);
+  }
+  s->merge_launches = iterations;
+  if ((rc = enqueue_final(s, (int)L, K, 1.0 - damping))) return rc;
+  cudaEventRecord(s->ev_end, st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "enqueue failed: %s", cudaGetErrorString(e));
+  return PPRB200_OK;
+}
+
+static int session_stats_impl(pprb200_session* s, pprb200_stats* out) {
+  if (!out) return fail(PPRB200_ERR_PARAM, "stats is NULL");
+  std::memset(out, 0, sizeof(*out));
+  if (s->last_mode < 0) return fail(PPRB200_ERR_STATE, "no run has been enqueued on this session");
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  RunState h;
+  unsigned long long fin[2];
+  CUDA_TRY(cudaMemcpy(&h, s->d_state, sizeof(h), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(fin, s->d_final_stats, sizeof(fin), cudaMemcpyDeviceToHost));
+  out->iterations_run = (uint32_t)h.iter;
+  out->n_gpus = (uint32_t)s->world;
+  uint64_t ni = 0;
+  if (s->last_mode == MODE_GRANK)
+    for (int i = 0; i < h.iter; i++) ni += (uint64_t)s->colour_count[i & 1];
+  else
+    ni = (uint64_t)h.iter * (uint64_t)s->n;
+  out->node_iterations = ni;
+  out->nonsink_node_iterations = h.node_iters;
+  out->edge_reads = h.edge_reads;
+  out->merged_entries = h.merged;
+  out->candidates = h.cands;
+  out->truncations = h.truncs + fin[0];
+  out->boundary_ties = h.ties + fin[1];
+  out->algorithmic_bytes = h.abytes;
+  out->walk_steps = h.walk_steps;
+  out->walks = h.walks;
+  out->overflow_requeues = h.requeues;
+  // maxDiff pair as grank.h leaves it: [0] = older, [1] = latest (after the swap of :140)
+  out->max_diff[0] = h.m_prev < 0 ? 0.0 : (double)h.m_prev * NORM_INV;
+  out->max_diff[1] = h.m_last < 0 ? 0.0 : (double)h.m_last * NORM_INV;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, s->ev_begin, s->ev_end) == cudaSuccess) out->kernel_ms = ms;
+  out->prep_ms = s->prep_ms;
+  out->h2d_ms = s->h2d_ms;
+  return PPRB200_OK;
+}
+
+static int session_fetch_impl(pprb200_session* s, int32_t* out_ids, double* out_scores, uint32_t* out_cnt) {
+  if (s->last_mode < 0) return fail(PPRB200_ERR_STATE, "no run has been enqueued on this session");
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  const size_t cnt = (size_t)s->n * s->last_K;
+  if (out_ids && cnt) CUDA_TRY(cudaMemcpyAsync(out_ids, s->d_out_ids, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+  if (out_scores && cnt) CUDA_TRY(cudaMemcpyAsync(out_scores, s->d_out_scores, cnt * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (out_cnt && s->n) CUDA_TRY(cudaMemcpyAsync(out_cnt, s->d_out_cnt, (size_t)s->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return PPRB200_OK;
+}
+
+static std::mutex g_api_mutex;  // one run at a time per process (SURVEY.md 8b re-entrancy)
+
+extern "C" {
+
+int pprb200_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int d = 0; d < cnt; d++) {
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, d) == cudaSuccess && pr.major == 10) ok++;
+  }
+  return ok;
+}
+
+int pprb200_session_create(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour, uint32_t max_L,
+                           uint32_t hub_threshold, int32_t rank, int32_t world, void* stream, pprb200_session** out) {
+  std::lock_guard<std::mutex> lk(g_api_mutex);
+  return session_create_impl(row_ptr, col, n, colour, max_L, hub_threshold, rank, world, stream, out);
+}
+
+void pprb200_session_destroy(pprb200_session* s) {
+  std::lock_guard<std::mutex> lk(g_api_mutex);
+  if (s) { cudaStreamSynchronize(s->stream); session_free(s); }
+}
+
+int pprb200_session_grank(pprb200_session* s, uint32_t K, uint32_t L, uint32_t iterations, double damping, double tolerance) {
+  if (!s) return fail(PPRB200_ERR_PARAM, "session is NULL");
+  std::lock_guard<std::mutex> lk(g_api_mutex);
+  return session_grank_impl(s, K, L, iterations, damping, tolerance);
+}
+
+int pprb200_session_mc(pprb200_session* s, uint32_t K, uint32_t L, uint32_t R, double damping, uint64_t seed, uint32_t rounds) {
+  (void)s; (void)K; (void)L; (void)R; (void)damping; (void)seed; (void)rounds;
+  return fail(PPRB200_ERR_STATE, "MC path not built yet");
+}
+
+int pprb200_session_fetch(pprb200_session* s, int32_t* out_ids, double* out_scores, uint32_t* out_cnt) {
+  if (!s) return fail(PPRB200_ERR_PARAM, "session is NULL");
+  std::lock_guard<std::mutex> lk(g_api_mutex);
+  return session_fetch_impl(s, out_ids, out_scores, out_cnt);
+}
+
+int pprb200_session_stats(pprb200_session* s, pprb200_stats* stats) {
+  if (!s) return fail(PPRB200_ERR_PARAM, "session is NULL");
+  std::lock_guard<std::mutex> lk(g_api_mutex);
+  return session_stats_impl(s, stats);
+}
+
+int pprb200_session_kernel_time(pprb200_session* s, int which, uint32_t* launches, double* total_ms) {
+  if (!s) return fail(PPRB200_ERR_PARAM, "session is NULL");
+  std::lock_guard<std::mutex> lk(g_api_mutex);
+  if (s->last_mode < 0) return fail(PPRB200_ERR_STATE, "no run has been enqueued on this session");
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (which != 0) return fail(PPRB200_ERR_PARAM, "which=%d unknown", which);
+  RunState h;
+  CUDA_TRY(cudaMemcpy(&h, s->d_state, sizeof(h), cudaMemcpyDeviceToHost));
+  double tot = 0;
+  uint32_t cnt = 0;
+  for (int i = 0; i < h.iter && (size_t)(2 * i + 1) < s->ev_merge.size(); i++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s->ev_merge[2 * i], s->ev_merge[2 * i + 1]) == cudaSuccess) { tot += ms; cnt++; }
+  }
+  if (launches) *launches = cnt;
+  if (total_ms) *total_ms = tot;
+  return PPRB200_OK;
+}
+
+int pprb200_grank(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour, uint32_t K, uint32_t L,
+                  uint32_t iterations, double damping, double tolerance, uint32_t hub_threshold, int32_t* out_ids,
+                  double* out_scores, uint32_t* out_cnt, pprb200_stats* stats) {
+  int rc = check_params(K, L, iterations, damping);  // before touching the graph (test/grankTest.cc:22-28)
+  if (rc) return rc;
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (n == 0) return PPRB200_OK;  // empty graph -> empty result (test/grankTest.cc:31-36)
+  const double t0 = now_ms();
+  pprb200_session* s = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    rc = session_create_impl(row_ptr, col, n, colour, L, hub_threshold, 0, 1, nullptr, &s);
+    if (rc) return rc;
+    rc = session_grank_impl(s, K, L, iterations, damping, tolerance);
+    double t_d2h = 0;
+    if (!rc) {
+      cudaStreamSynchronize(s->stream);
+      const double t1 = now_ms();
+      rc = session_fetch_impl(s, out_ids, out_scores, out_cnt);
+      t_d2h = now_ms() - t1;
+    }
+    if (!rc && stats) {
+      rc = session_stats_impl(s, stats);
+      stats->d2h_ms = t_d2h;
+    }
+    session_free(s);
+  }
+  if (!rc && stats) stats->total_ms = now_ms() - t0;
+  return rc;
+}
+
+int pprb200_mccompletepathv2(const int64_t* row_ptr, const int32_t* col, int32_t n, uint32_t K, uint32_t L, uint32_t R,
+                             double damping, uint64_t seed, uint32_t rounds, uint32_t hub_threshold, int32_t* out_ids,
+                             double* out_scores, uint32_t* out_cnt, pprb200_stats* stats) {
+  (void)row_ptr; (void)col; (void)n; (void)seed; (void)rounds; (void)hub_threshold; (void)out_ids; (void)out_scores; (void)out_cnt; (void)stats;
+  int rc = check_params(K, L, R, damping);
+  if (rc) return rc;
+  return fail(PPRB200_ERR_STATE, "MC path not built yet");
+}
+
+}  // extern "C"
