@@ -94,6 +94,8 @@ def load():
     lib.pprb200_session_fetch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
     lib.pprb200_session_stats.argtypes = [c_void_p, c_void_p]
     lib.pprb200_session_kernel_time.argtypes = [c_void_p, c_int, C.POINTER(c_uint32), C.POINTER(c_double)]
+    lib.pprb200_session_launches.argtypes = [c_void_p, C.POINTER(c_uint64)]
+    lib.pprb200_session_launches.restype = c_int
     lib.pprb200_gen_rmat.argtypes = [c_uint32, c_uint32, c_uint64, c_double, c_double, c_double, c_void_p, c_void_p]
     lib.pprb200_gen_ba.argtypes = [c_int32, c_uint32, c_uint64, c_void_p, c_void_p, C.POINTER(c_int64)]
     for name in ("pprb200_find_partitions", "pprb200_grank", "pprb200_mccompletepathv2", "pprb200_session_create",

@@ -159,6 +159,11 @@ class Session:
         _lib.check(self.lib.pprb200_session_kernel_time(self.handle, which, C.byref(launches), C.byref(ms)))
         return launches.value, ms.value
 
+    def launches(self) -> int:
+        v = C.c_uint64(0)
+        _lib.check(self.lib.pprb200_session_launches(self.handle, C.byref(v)))
+        return v.value
+
     def close(self):
         if self.handle:
             self.lib.pprb200_session_destroy(self.handle)

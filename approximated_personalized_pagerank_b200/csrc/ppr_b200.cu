@@ -186,6 +186,7 @@ struct pprb200_session {
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   std::vector<cudaEvent_t> ev_merge;  // pairs (begin,end) per iteration
   uint32_t merge_launches = 0;
+  uint64_t launch_count = 0;  // kernels enqueued by the last run
   double prep_ms = 0, h2d_ms = 0;
 };
 
@@ -342,7 +343,7 @@ static unsigned int next_pow2(unsigned long long x) {
 }
 
 template <int CAP, int WARPS, typename IdxT>
-static cudaError_t launch_stage(const pprb200_session* s, const MergeParams& P, int grid, size_t smem, unsigned char* ws,
+static cudaError_t launch_stage(pprb200_session* s, const MergeParams& P, int grid, size_t smem, unsigned char* ws,
                                 unsigned int ws_cap, int ws_identity) {
   static bool configured = false;
   if (!configured) {
@@ -351,6 +352,7 @@ static cudaError_t launch_stage(const pprb200_session* s, const MergeParams& P, 
     configured = true;
   }
   merge_seq_kernel<CAP, WARPS, IdxT><<<grid, WARPS * 32, smem, s->stream>>>(P, ws, ws_cap, ws_identity);
+  s->launch_count++;
   return cudaGetLastError();
 }
 
@@ -434,7 +436,7 @@ static int ensure_outputs(pprb200_session* s, uint32_t K) {
 
 static int enqueue_final(pprb200_session* s, int L, uint32_t K, double sink_score) {
   const int Lp = roundup4(L);
-  const int warps = 8;
+  const int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(200 * 1024) / ((size_t)Lp * 12)));
   const size_t smem = (size_t)warps * Lp * 12;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
@@ -447,6 +449,7 @@ static int enqueue_final(pprb200_session* s, int L, uint32_t K, double sink_scor
   final_topk_kernel<<<grid, warps * 32, smem, s->stream>>>(s->d_pos_of, s->d_colour, s->d_buf[0], s->d_buf[1], s->d_state,
                                                            s->n, Lp, (int)K, sink_score, s->d_out_ids, s->d_out_scores,
                                                            s->d_out_cnt, s->d_final_stats);
+  s->launch_count++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "final_topk launch failed: %s", cudaGetErrorString(e));
   return PPRB200_OK;
@@ -466,7 +469,7 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
   int rc = check_params(K, L, iterations, damping);
   if (rc) return rc;
   if (L > s->max_L) return fail(PPRB200_ERR_PARAM, "L=%u exceeds the session's max_L=%u", L, s->max_L);
-  if ((size_t)roundup4((int)L) * 12 * 8 > 200 * 1024) return fail(PPRB200_ERR_PARAM, "L=%u too large for the final top-K kernel", L);
+  if ((size_t)roundup4((int)L) * 12 > 200 * 1024) return fail(PPRB200_ERR_PARAM, "L=%u is above this build's limit of 17064", L);
   if ((rc = ensure_outputs(s, K))) return rc;
   s->last_mode = MODE_GRANK;
   s->last_K = K; s->last_L = L; s->last_iterations = iterations;
@@ -476,6 +479,7 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
   cudaStream_t st = s->stream;
   cudaEventRecord(s->ev_begin, st);
   state_reset_kernel<<<1, 1, 0, st>>>(s->d_state);
+  s->launch_count = 1;
   MergeParams P;
   std::memset(&P, 0, sizeof(P));
   P.g.row_off = s->d_row_off; P.g.col = s->d_col; P.g.label = s->d_label;
@@ -494,6 +498,7 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
       Q.init_mode = 1; Q.do_norm = 0; Q.colour = c;
       if ((rc = enqueue_cascade(s, Q, s->range_begin[c], s->range_end[c], (int)L))) return rc;
       phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 1, 0);
+      s->launch_count++;
     }
   }
   for (uint32_t it = 0; it < iterations; it++) {
@@ -506,6 +511,7 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
     }
     cudaEventRecord(s->ev_merge[2 * it + 1], st);
     iter_end_kernel<<<1, 1, 0, st>>>(s->d_state, c, tolerance);
+    s->launch_count++;
   }
   s->merge_launches = iterations;
   if ((rc = enqueue_final(s, (int)L, K, 1.0 - damping))) return rc;
@@ -628,6 +634,12 @@ int pprb200_session_kernel_time(pprb200_session* s, int which, uint32_t* launche
   }
   if (launches) *launches = cnt;
   if (total_ms) *total_ms = tot;
+  return PPRB200_OK;
+}
+
+int pprb200_session_launches(pprb200_session* s, uint64_t* launches) {
+  if (!s || !launches) return fail(PPRB200_ERR_PARAM, "NULL argument");
+  *launches = s->launch_count;
   return PPRB200_OK;
 }
 

@@ -123,6 +123,9 @@ int pprb200_session_stats(pprb200_session* s, pprb200_stats* stats);
  * stream: which = 0 merge (GRank iterations / MC combine), 1 MC walks. Returns launches and total ms. */
 int pprb200_session_kernel_time(pprb200_session* s, int which, uint32_t* launches, double* total_ms);
 
+/* Kernels the last run enqueued on the session stream (bench.py's gpu_launches). */
+int pprb200_session_launches(pprb200_session* s, uint64_t* launches);
+
 /* ---- synthetic workloads of BASELINE.json (host only; used by bench.py and the tests) --------------- */
 
 /* R-MAT (a,b,c,1-a-b-c), 2^scale nodes, edge_factor*2^scale directed edges, duplicates and self-loops

@@ -1,0 +1,190 @@
+"""GPU parity tests of the GRank path (run with -m gpu on a B200). Everything goes through the C-ABI
+(pprb200_grank / session API) and is checked against the oracle bit for bit, against the reference's golden
+vectors (<= 1e-9, identical membership) and against the reference's own unit-test expectations."""
+import numpy as np
+import pytest
+
+import oracle_bindings as ob
+import approximated_personalized_pagerank_b200 as ppr
+from approximated_personalized_pagerank_b200 import graphs as G
+from conftest import golden_cases, load_golden
+from helpers import assert_bit_identical, compare_membership
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9  # north-star tolerance for GRank scores (fp64)
+
+
+def run_pair(g, K, L, it, d, tol, hub=None):
+    """GPU and oracle on the same input, same partition, same hub threshold."""
+    colour = ppr.find_partitions_csr(g)
+    gpu_hub = ppr.NEVER_HUB if hub is None else hub
+    got = ppr.grank_csr(g, K, L, it, d, tol, colour=colour, hub_threshold=gpu_hub)
+    want = ob.oracle_grank(g, K, L, it, d, tol, colour=colour, hub_threshold=0 if hub is None else hub)
+    return got, want
+
+
+STAT_KEYS = ["iterations_run", "node_iterations", "nonsink_node_iterations", "edge_reads", "merged_entries", "candidates",
+             "truncations", "boundary_ties", "algorithmic_bytes"]
+
+
+def assert_same_stats(got, want):
+    for k in STAT_KEYS:
+        assert got.stats[k] == want.stats[k], (k, got.stats[k], want.stats[k])
+
+
+@pytest.mark.parametrize("name", golden_cases("grank"))
+def test_golden_reference_vectors(name):
+    """GPU vs the unmodified reference's output (tie-free fixtures): identical membership, |d| <= 1e-9"""
+    g, z = load_golden(name)
+    order = z["order"]
+    gd = g.relabel(order)
+    got = ppr.grank_csr(gd, int(z["K"]), int(z["L"]), int(z["iterations"]), float(z["damping"]), float(z["tolerance"]),
+                        colour=None, hub_threshold=ppr.NEVER_HUB)   # colour=None: the library's own findPartitions
+    gk = ob.baskets_to_keyspace(got, order)
+    assert (gk.cnt == np.minimum(z["cnt"], int(z["K"]))).all()
+    mism, maxd = compare_membership(gk, ob.Result(z["ids"], z["scores"], z["cnt"]))
+    assert mism == 0
+    assert maxd <= TOL
+    assert maxd == 0.0  # in fact bit-identical: same fma chain in the same order
+
+
+@pytest.mark.parametrize("scale,K,L,it,tol", [(8, 50, 100, 30, 1e-3), (10, 50, 100, 30, 1e-3), (10, 1, 1, 10, -1.0),
+                                              (10, 7, 9, 12, 1e-4), (10, 50, 50, 8, -1.0), (11, 20, 101, 10, -1.0),
+                                              (10, 50, 300, 10, -1.0), (9, 512, 512, 20, -1.0), (12, 50, 100, 30, 1e-3),
+                                              (13, 50, 100, 6, -1.0)])
+def test_bit_identical_to_oracle_on_rmat(scale, K, L, it, tol):
+    """heavy-tailed graphs with thousands of boundary ties: the canonical tie-break makes the result unique"""
+    got, want = run_pair(G.rmat(scale), K, L, it, 0.85, tol)
+    assert_bit_identical(got, want, f"rmat{scale} K{K} L{L}")
+    assert_same_stats(got, want)
+
+
+@pytest.mark.parametrize("damping", [0.0, 0.5, 1.0])
+def test_damping_edge_values(damping):
+    got, want = run_pair(G.rmat(9), 20, 40, 8, damping, -1.0)
+    assert_bit_identical(got, want, f"damping {damping}")
+
+
+@pytest.mark.parametrize("tol", [0.01, 0.0005, 1e-5, 0.001, 0.0, -1.0])
+def test_convergence_stops_at_the_same_iteration(tol):
+    """grankMultiThreadTest.cc:384-479 uses these tolerances; the device-side flag must stop where the oracle does"""
+    rng = np.random.default_rng(5)
+    g = G.from_edges(300, rng.integers(0, 300, 2000), rng.integers(0, 300, 2000))
+    got, want = run_pair(g, 300, 300, 60, 0.85, tol)
+    assert got.stats["iterations_run"] == want.stats["iterations_run"]
+    assert_bit_identical(got, want, f"tol {tol}")
+
+
+def test_single_iteration_and_two_iterations():
+    g = G.rmat(9)
+    for it in (1, 2, 3):
+        got, want = run_pair(g, 30, 60, it, 0.85, 10.0)  # huge tolerance: still at least 2 iterations when allowed
+        assert got.stats["iterations_run"] == want.stats["iterations_run"] == min(it, 2)
+        assert_bit_identical(got, want, f"iterations {it}")
+
+
+def test_multi_edges_and_self_loops_count():
+    """test/grankTest.cc:60,79: duplicates and self loops are weighted by multiplicity"""
+    g = G.from_edges(5, [0, 0, 0, 1, 1, 2, 3, 3, 3, 3], [1, 1, 0, 2, 2, 2, 4, 4, 4, 0])
+    got, want = run_pair(g, 5, 5, 50, 0.85, -1.0)
+    assert_bit_identical(got, want, "multigraph")
+
+
+def test_ragged_and_degenerate_graphs():
+    for g in (G.from_edges(1, [], []), G.from_edges(1, [0], [0]), G.from_edges(2, [0, 1], [1, 0]), G.from_edges(10, [], []),
+              G.from_edges(40, [0] * 39, list(range(1, 40))), G.from_edges(40, list(range(1, 40)), [0] * 39)):
+        got, want = run_pair(g, 10, 30, 20, 0.85, 1e-4)
+        assert_bit_identical(got, want, f"n={g.n} e={g.n_edges}")
+
+
+def test_big_L_uses_the_global_table_stage():
+    """L > N and L large enough that no shared-memory table class is usable"""
+    got, want = run_pair(G.rmat(8), 300, 5000, 6, 0.85, -1.0)
+    assert_bit_identical(got, want, "L=5000")
+
+
+def test_deterministic_run_to_run():
+    g = G.rmat(11)
+    a = ppr.grank_csr(g, 50, 100, 10, 0.85, -1.0)
+    b = ppr.grank_csr(g, 50, 100, 10, 0.85, -1.0)
+    assert_bit_identical(a, b, "repeat")
+
+
+# ---- the reference's own unit tests, re-expressed through the dict API (test/grankTest.cc) ----
+def test_ref_no_edges_single_node_two_nodes():
+    res = ppr.grank({i: [] for i in range(10)}, 10, 30, 100, 0.85, 1e-4)            # :38-50
+    assert len(res) == 10 and all(len(res[i]) == 1 and abs(res[i][i] - 0.15) < 10e-5 for i in range(10))
+    res = ppr.grank({0: [0]}, 10, 30, 100, 0.85, 1e-4)                               # :70-84
+    assert abs(res[0][0] - 1.0) < 10e-5
+    res = ppr.grank({0: [1], 1: [0]}, 10, 30, 100, 0.85, 1e-4)                       # :86-105
+    assert len(res[0]) == 2 and res[0][0] > res[0][1] and res[1][1] > res[1][0]
+
+
+def test_ref_top_l_sizes():
+    rng = np.random.default_rng(3)                                                   # :52-68
+    graph = {i: [] for i in range(30)}
+    for _ in range(30):
+        graph[int(rng.integers(30))].append(int(rng.integers(30)))
+    for i in range(1, 30, 4):
+        res = ppr.grank(graph, i, i, 100, 0.85, 1e-4)
+        assert len(res) == 30 and all(len(b) <= i for b in res.values())
+
+
+def test_ref_line_and_ring_monotone():
+    graph = {i: [(i + 1) % 6] for i in range(6)}                                     # :107-152
+    for K, L in ((10, 30), (3, 4), (3, 3)):
+        res = ppr.grankMulti(graph, K, L, 100, 0.85, 1e-4, 4)
+        for i in range(6):
+            size = min(K, 6)
+            assert len(res[i]) == size
+            for u in range(min(size, 3) - 1 if K == 3 else size - 1):
+                # the reference reads with operator[]: a missing key reads as 0 (L=4 wraps the truncated tail around)
+                assert res[i].get((i + u) % 6, 0.0) > res[i].get((i + u + 1) % 6, 0.0)
+    graph = {i: [(i + 1) % 100] for i in range(100)}                                 # :184-283
+    for K, L, tol in ((10, 10, 1e-4), (10, 20, 1e-4), (10, 100, 1e-4), (100, 100, -1), (200, 200, -1)):
+        res = ppr.grank(graph, K, L, 100, 0.85, tol)
+        for i in range(100):
+            size = min(K, 100)
+            assert len(res[i]) == size
+            for u in range(size - 1):
+                assert res[i].get((i + u + 1) % 100, 0.0) > 0 and res[i].get((i + u) % 100, 0.0) > res[i].get((i + u + 1) % 100, 0.0)
+
+
+def test_ref_star():
+    graph = {i: ([0] if i else []) for i in range(6)}                                # :154-182
+    res = ppr.grank(graph, 10, 30, 100, 0.85, 1e-4)
+    assert len(res[0]) == 1 and abs(res[0][0] - 0.15) < 10e-5
+    assert all(len(res[i]) == 2 and abs(res[i][0] - 0.15 * 0.85) < 10e-5 for i in range(1, 6))
+    graph[0].append(0)
+    res = ppr.grank(graph, 10, 30, 100, 0.85, 1e-4)
+    assert all(len(res[i]) == 2 and abs(res[i][0] - 0.85) < 10e-5 for i in range(1, 6))
+
+
+@pytest.mark.parametrize("name", ["ppr_ring100", "ppr_rmat10"])
+def test_ref_same_as_pagerank(name):
+    """:285-379 -- K=L=N, tol -1, 100 iterations equals pprSingleSource (golden, from the reference) within 10e-5"""
+    g, z = load_golden(name)
+    n = g.n
+    got = ppr.grank_csr(g, n, n, 100, 0.85, -1.0, hub_threshold=ppr.NEVER_HUB)
+    for i, s in enumerate(z["sources"]):
+        dense = np.zeros(n)
+        dense[got.ids[s, :got.cnt[s]]] = got.scores[s, :got.cnt[s]]
+        assert np.abs(dense - z["ppr"][i]).max() < 10e-5
+
+
+# ---- BASELINE full size: bit parity (the oracle finishes R-MAT-16 in seconds) + size-independent properties ----
+def test_rmat16_full_config_bit_identical_and_properties():
+    g = G.rmat(16)
+    got, want = run_pair(g, 50, 100, 30, 0.85, 1e-3)
+    assert_bit_identical(got, want, "rmat16")
+    assert_same_stats(got, want)
+    sc, ids, cnt = got.scores, got.ids, got.cnt
+    valid = np.arange(50)[None, :] < cnt[:, None]
+    assert (np.diff(sc, axis=1)[valid[:, 1:]] <= 0).all()                       # sorted descending
+    assert ((sc >= 0) & (sc <= 1)).all() and (sc.sum(1) <= 1 + 1e-12).all()     # PPR mass
+    assert (ids[~valid] == -1).all() and (ids[valid] >= 0).all() and (ids[valid] < g.n).all()
+    sinks = g.out_degree() == 0
+    assert (cnt[sinks] == 1).all() and (ids[sinks, 0] == np.nonzero(sinks)[0]).all() and np.allclose(sc[sinks, 0], 0.15, atol=1e-15)
+    srt = np.sort(np.where(valid, ids, np.arange(-50, 0)[None, :]), axis=1)
+    assert (np.diff(srt, axis=1) != 0).all()                                    # keys unique inside a basket
