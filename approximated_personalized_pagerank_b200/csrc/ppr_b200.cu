@@ -12,7 +12,7 @@
 #include <numeric>
 #include <vector>
 
-#include "merge_seq.cuh"
+#include "merge_par.cuh"
 #include "ppr_internal.h"
 
 namespace pprb200 {
@@ -158,8 +158,24 @@ struct pprb200_session {
   int rank = 0, world = 1;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
-  // storage ranges [colour]: all non-sink nodes of that colour (seq class first, then hub class)
+  // storage ranges [colour]: exact-order class (out-degree <= hub_threshold), stored first
   int range_begin[2] = {0, 0}, range_end[2] = {0, 0};
+  // order-free class (out-degree > hub_threshold): work items [colour][0 = mid (128-thread CTAs), 1 = big (512)]
+  int item_begin[2][2] = {{0, 0}, {0, 0}}, item_end[2][2] = {{0, 0}, {0, 0}};
+  int n_items = 0;
+  int chunk = 1024, mid_deg = 64;
+  int* d_item_pos = nullptr;
+  long long* d_item_off = nullptr;
+  int* d_item_len = nullptr;
+  unsigned char* d_pool = nullptr;
+  size_t tbl_bytes = 0;
+  unsigned int capmax = 0;
+  int n_tables = 0;
+  unsigned int* d_tbl_inuse = nullptr;
+  unsigned int* d_tbl_count = nullptr;
+  unsigned int* d_node_tbl = nullptr;
+  unsigned int* d_node_done = nullptr;
+  int32_t max_deg_seq = 0, max_deg_par = 0;
   int32_t colour_count[2] = {0, 0};  // all nodes (sinks included) per colour
   int32_t max_deg = 0;
   // device
@@ -220,6 +236,8 @@ static void session_free(pprb200_session* s) {
   for (int i = 0; i < 3; i++) cudaFree(s->d_queue[i]);
   cudaFree(s->d_ncand); cudaFree(s->d_state); cudaFree(s->d_final_stats); cudaFree(s->d_ws);
   cudaFree(s->d_out_ids); cudaFree(s->d_out_scores); cudaFree(s->d_out_cnt);
+  cudaFree(s->d_item_pos); cudaFree(s->d_item_off); cudaFree(s->d_item_len); cudaFree(s->d_pool);
+  cudaFree(s->d_tbl_inuse); cudaFree(s->d_tbl_count); cudaFree(s->d_node_tbl); cudaFree(s->d_node_done);
   if (s->ev_begin) cudaEventDestroy(s->ev_begin);
   if (s->ev_end) cudaEventDestroy(s->ev_end);
   for (auto e : s->ev_merge) cudaEventDestroy(e);
@@ -258,18 +276,30 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
     s->colour_count[colour[v]]++;
   }
 
-  // storage order: colour-major, out-degree descending (ties by dense id) -- big nodes first for load balance
+  // storage order: colour-major; inside a colour the exact-order class first, then the order-free class
+  // (mid, big); every class by out-degree descending (ties by dense id) -- big nodes first for load balance
+  if (const char* e = getenv("PPRB200_CHUNK")) s->chunk = std::max(32, atoi(e));
+  if (const char* e = getenv("PPRB200_MID_DEG")) s->mid_deg = std::max(1, atoi(e));
   std::vector<int32_t> order;
   order.reserve((size_t)n);
+  int cls_begin[2][3], cls_end[2][3];
   for (int c = 0; c < 2; c++) {
-    s->range_begin[c] = (int)order.size();
-    const size_t b = order.size();
-    for (int32_t v = 0; v < n; v++)
-      if (colour[v] == c && row_ptr[v + 1] > row_ptr[v]) order.push_back(v);
-    std::stable_sort(order.begin() + (long)b, order.end(), [&](int32_t x, int32_t y) {
-      return (row_ptr[x + 1] - row_ptr[x]) > (row_ptr[y + 1] - row_ptr[y]);
-    });
-    s->range_end[c] = (int)order.size();
+    for (int cls = 0; cls < 3; cls++) {
+      const size_t b = order.size();
+      cls_begin[c][cls] = (int)b;
+      for (int32_t v = 0; v < n; v++) {
+        const int64_t d = row_ptr[v + 1] - row_ptr[v];
+        if (colour[v] != c || d == 0) continue;
+        const int k = (uint64_t)d <= (uint64_t)s->hub_threshold ? 0 : (d <= s->mid_deg ? 1 : 2);
+        if (k == cls) order.push_back(v);
+      }
+      std::stable_sort(order.begin() + (long)b, order.end(), [&](int32_t x, int32_t y) {
+        return (row_ptr[x + 1] - row_ptr[x]) > (row_ptr[y + 1] - row_ptr[y]);
+      });
+      cls_end[c][cls] = (int)order.size();
+    }
+    s->range_begin[c] = cls_begin[c][0];
+    s->range_end[c] = cls_end[c][0];
   }
   const int32_t M = (int32_t)order.size();
   s->M = M;
@@ -283,6 +313,27 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   }
   const int64_t E = row_off[M];
   s->E = E;
+  std::vector<int> item_pos;
+  std::vector<long long> item_off;
+  std::vector<int> item_len;
+  for (int c = 0; c < 2; c++)
+    for (int cls = 1; cls < 3; cls++) {
+      s->item_begin[c][cls - 1] = (int)item_pos.size();
+      for (int p = cls_begin[c][cls]; p < cls_end[c][cls]; p++) {
+        const long long d = row_off[(size_t)p + 1] - row_off[p];
+        if (d > s->max_deg_par) s->max_deg_par = (int32_t)std::min<long long>(d, INT32_MAX);
+        for (long long o = 0; o < d; o += s->chunk) {
+          item_pos.push_back(p);
+          item_off.push_back(row_off[p] + o);
+          item_len.push_back((int)std::min<long long>(s->chunk, d - o));
+        }
+      }
+      s->item_end[c][cls - 1] = (int)item_pos.size();
+    }
+  s->n_items = (int)item_pos.size();
+  for (int c = 0; c < 2; c++)
+    for (int p = s->range_begin[c]; p < s->range_end[c]; p++)
+      s->max_deg_seq = std::max<int32_t>(s->max_deg_seq, (int32_t)std::min<long long>(row_off[(size_t)p + 1] - row_off[p], INT32_MAX));
   std::vector<uint32_t> enc((size_t)std::max<int64_t>(E, 1));
   for (int32_t p = 0; p < M; p++) {
     const int32_t v = order[p];
@@ -319,6 +370,36 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   if (M) UP(s->d_label, order.data(), (size_t)M * sizeof(int));
   if (n) UP(s->d_pos_of, pos_of.data(), (size_t)n * sizeof(int));
   if (n) UP(s->d_colour, colour.data(), (size_t)n);
+  if (s->n_items > 0) {
+    const int Lpm = roundup4((int)max_L);
+    const unsigned long long worst = std::min<unsigned long long>(2ull * ((unsigned long long)s->max_deg_par * Lpm + 2ull),
+                                                                  2ull * ((unsigned long long)n + 1ull));
+    unsigned int cap = 1024;
+    while ((unsigned long long)cap < worst) cap <<= 1;
+    s->capmax = cap;
+    s->n_tables = s->sm_count * 3 + 8;  // >= CTAs in flight of either merge_par instantiation
+    s->tbl_bytes = (size_t)cap * (sizeof(GSlot) + sizeof(unsigned int));
+    if ((rc = dev_alloc(&s->d_item_pos, (size_t)s->n_items)) || (rc = dev_alloc(&s->d_item_off, (size_t)s->n_items)) ||
+        (rc = dev_alloc(&s->d_item_len, (size_t)s->n_items)) || (rc = dev_alloc(&s->d_pool, s->tbl_bytes * (size_t)s->n_tables)) ||
+        (rc = dev_alloc(&s->d_tbl_inuse, (size_t)s->n_tables)) || (rc = dev_alloc(&s->d_tbl_count, (size_t)s->n_tables)) ||
+        (rc = dev_alloc(&s->d_node_tbl, (size_t)M)) || (rc = dev_alloc(&s->d_node_done, (size_t)M))) {
+      session_free(s);
+      return rc;
+    }
+    UP(s->d_item_pos, item_pos.data(), (size_t)s->n_items * sizeof(int));
+    UP(s->d_item_off, item_off.data(), (size_t)s->n_items * sizeof(long long));
+    UP(s->d_item_len, item_len.data(), (size_t)s->n_items * sizeof(int));
+    cudaMemsetAsync(s->d_tbl_inuse, 0, (size_t)s->n_tables * sizeof(unsigned int), st);
+    cudaMemsetAsync(s->d_tbl_count, 0, (size_t)s->n_tables * sizeof(unsigned int), st);
+    cudaMemsetAsync(s->d_node_tbl, 0, (size_t)M * sizeof(unsigned int), st);
+    cudaMemsetAsync(s->d_node_done, 0, (size_t)M * sizeof(unsigned int), st);
+    // pool tables: keys -1 / acc 0. GSlot = {key, pad, acc}: fill with 0xff then zero the acc words
+    for (int t = 0; t < s->n_tables; t++) {
+      unsigned char* base = s->d_pool + (size_t)t * s->tbl_bytes;
+      cudaMemset2DAsync(base, sizeof(GSlot), 0xff, 8, cap, st);
+      cudaMemset2DAsync(base + 8, sizeof(GSlot), 0x00, 8, cap, st);
+    }
+  }
 #undef UP
   cudaError_t e = cudaStreamSynchronize(st);  // host vectors go out of scope
   if (e != cudaSuccess) { session_free(s); return fail(PPRB200_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e)); }
@@ -395,7 +476,7 @@ static int enqueue_cascade(pprb200_session* s, MergeParams P, int range_begin, i
     else { Q.queue_in = s->d_queue[qsrc]; Q.queue_in_idx = qsrc; }
     Q.queue_out = nullptr;
     Q.queue_out_idx = 0;
-    const unsigned long long bound = std::min<unsigned long long>((unsigned long long)s->max_deg * (unsigned long long)Lp + 2ull + 32ull,
+    const unsigned long long bound = std::min<unsigned long long>((unsigned long long)s->max_deg_seq * (unsigned long long)Lp + 2ull + 32ull,
                                                                   (unsigned long long)s->n + 1ull);
     unsigned int cap;
     int identity;
@@ -417,6 +498,54 @@ static int enqueue_cascade(pprb200_session* s, MergeParams P, int range_begin, i
     }
     cudaError_t e = launch_stage<0, 4, unsigned int>(s, Q, grid, (size_t)warps_g * 1040, s->d_ws, cap, identity);
     if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "global merge stage launch failed: %s", cudaGetErrorString(e));
+  }
+  return PPRB200_OK;
+}
+
+template <int CAP, int THREADS>
+static cudaError_t launch_par(pprb200_session* s, const ParParams& P, int grid) {
+  const size_t smem = (size_t)CAP * 14 + sizeof(ParShared);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(merge_par_kernel<CAP, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  merge_par_kernel<CAP, THREADS><<<grid, THREADS, smem, s->stream>>>(P);
+  s->launch_count++;
+  return cudaGetLastError();
+}
+
+// Enqueue the order-free path for the nodes of colour c above the hub threshold: hub chunks / big nodes on
+// 512-thread CTAs (1 per SM), mid-degree nodes on 128-thread CTAs (3 per SM).
+static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
+  ParParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.M = M;
+  P.M.Lp = roundup4(L);
+  P.M.L = L;
+  P.M.colour = c;
+  P.chunk = s->chunk;
+  P.pool = s->d_pool;
+  P.tbl_bytes = s->tbl_bytes;
+  P.capmax = s->capmax;
+  P.n_tables = s->n_tables;
+  P.tbl_inuse = s->d_tbl_inuse;
+  P.tbl_count = s->d_tbl_count;
+  P.node_tbl = s->d_node_tbl;
+  P.node_done = s->d_node_done;
+  P.n_ids = s->n;
+  for (int cls = 1; cls >= 0; cls--) {
+    const int b = s->item_begin[c][cls], e = s->item_end[c][cls];
+    if (e == b) continue;
+    P.item_pos = s->d_item_pos + b;
+    P.item_begin = s->d_item_off + b;
+    P.item_len = s->d_item_len + b;
+    P.n_items = e - b;
+    P.work_idx = 4 + cls;
+    cudaError_t err = cls == 1 ? launch_par<16384, 512>(s, P, std::min(s->sm_count, e - b))
+                               : launch_par<4096, 128>(s, P, std::min(s->sm_count * 3, e - b));
+    if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_par launch failed: %s", cudaGetErrorString(err));
   }
   return PPRB200_OK;
 }
@@ -493,10 +622,10 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
     // init (grank.h:64-83)
     cudaMemsetAsync(s->d_ncand, 0, (size_t)s->M * sizeof(int), st);
     for (int c = 0; c < 2; c++) {
-      if (s->range_end[c] == s->range_begin[c]) continue;
       MergeParams Q = P;
       Q.init_mode = 1; Q.do_norm = 0; Q.colour = c;
-      if ((rc = enqueue_cascade(s, Q, s->range_begin[c], s->range_end[c], (int)L))) return rc;
+      if ((rc = enqueue_par(s, Q, c, (int)L))) return rc;
+      if (s->range_end[c] > s->range_begin[c] && (rc = enqueue_cascade(s, Q, s->range_begin[c], s->range_end[c], (int)L))) return rc;
       phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 1, 0);
       s->launch_count++;
     }
@@ -504,10 +633,11 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
   for (uint32_t it = 0; it < iterations; it++) {
     const int c = (int)(it & 1);  // partitions.first on even iterations (grank.h:96,129)
     cudaEventRecord(s->ev_merge[2 * it], st);
-    if (s->range_end[c] > s->range_begin[c]) {
+    {
       MergeParams Q = P;
       Q.init_mode = 0; Q.do_norm = 1; Q.colour = c;
-      if ((rc = enqueue_cascade(s, Q, s->range_begin[c], s->range_end[c], (int)L))) return rc;
+      if ((rc = enqueue_par(s, Q, c, (int)L))) return rc;
+      if (s->range_end[c] > s->range_begin[c] && (rc = enqueue_cascade(s, Q, s->range_begin[c], s->range_end[c], (int)L))) return rc;
     }
     cudaEventRecord(s->ev_merge[2 * it + 1], st);
     iter_end_kernel<<<1, 1, 0, st>>>(s->d_state, c, tolerance);
