@@ -6,8 +6,10 @@
 //   * row_off[M+1] (int64) / col[E'] (uint32): CSR in storage order. A col word is
 //        sink successor      : 0x80000000 | dense id of the sink
 //        non-sink successor  : storage position | colour << 30
-//   * label[M]: dense (external) id of the node at position p. Basket entries carry dense ids, so the
-//     canonical tie-break (score desc, dense id asc) is independent of the storage order.
+//   * Basket entries carry "rank labels": nodes numbered by in-degree descending (ties by dense id), so that the
+//     most popular keys are the smallest integers (merge_par.cuh indexes a dense accumulator with them).
+//     label[M] = rank label of the node at position p; dense_of[n] maps a label back to the dense (external) id,
+//     which the canonical tie-break (score desc, dense id asc) and the final output use.
 //   * baskets: two buffers of M slots; a slot is Lp = roundup4(L) entries stored as
 //        int32 ids[Lp] | double scoreA[Lp/2] | double scoreB[Lp/2]
 //     where entry e = 4g + r keeps its score in scoreA[2g + r] (r < 2) or scoreB[2g + r - 2] (r >= 2), so
@@ -49,7 +51,8 @@ struct RunState {
 struct GraphDev {
   const long long* row_off;  // [M+1]
   const uint32_t* col;       // [E']
-  const int* label;          // [M]
+  const int* label;          // [M] rank label of the node stored at position p
+  const int* dense_of;       // [n] rank label -> dense (external) id, for the canonical tie-break and the output
 };
 
 __host__ __device__ inline int roundup4(int x) { return (x + 3) & ~3; }

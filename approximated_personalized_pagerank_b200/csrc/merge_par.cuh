@@ -6,22 +6,18 @@
 // several CTAs -- accumulate concurrently with atomics and still produce bit-identical sums
 // (oracle/ppr_oracle.c applies the same rounding). |difference to the reference's fma chain| <= outdeg * 2^-62.
 //
-// Accumulator hierarchy:
-//   1. shared memory open-addressing table of the CTA, PAR_CAP slots: int32 key + 2 x uint32 fixed-point
-//      words (ATOMS.ADD.32 on the low word, carry into the high word) + list of occupied slots;
-//      filled first come first served up to PAR_LIMIT distinct keys;
-//   2. when the node has more candidates than that, or is split into several chunks, a global (L2-resident)
-//      table taken from a small pool: entries that miss the full shared table are added there directly
-//      (CAS on the key, RED.ADD.64 on the value) and at the end of the chunk the shared table is flushed into it.
-//      The CTA that completes the last chunk of a node selects the top-L from the global table.
+// Basket keys are "rank labels": nodes numbered by in-degree descending. On power-law graphs 93-98 % of all
+// merged entries carry one of the ~12 K most popular keys (profiles/README.md), so the accumulator is
+//   1. DENSE: a direct-mapped shared-memory array of H fixed-point words for labels < H -- no hashing, no key
+//      compare, no insertion: one ATOMS.ADD.32 on the low word, the carry into the high word;
+//   2. TAIL: a shared-memory open-addressing table (TCAP slots) for the other labels, first come first served;
+//   3. GLOBAL: when the tail outgrows its table, or the node is split into several chunks, a table from a small
+//      L2-resident pool; chunk CTAs flush their shared accumulators into it and the CTA that completes the last
+//      chunk of the node selects the top-L.
 #pragma once
 #include "merge_seq.cuh"
 
 namespace pprb200 {
-
-// Two instantiations: <16384 slots, 512 threads> (1 CTA/SM) for big nodes and chunks of hubs, and
-// <4096 slots, 128 threads> (3 CTAs/SM) for mid-degree nodes. PAR_LIMIT distinct keys are admitted to the shared
-// table (concurrent inserts may overshoot by < THREADS).
 
 struct GSlot {
   int key;
@@ -40,26 +36,27 @@ struct ParParams {
   // global table pool
   unsigned char* pool;
   size_t tbl_bytes;
-  unsigned int capmax;         // slots per pool table (power of two >= 2(n+1))
+  unsigned int capmax;         // slots per pool table (power of two)
   int n_tables;
   unsigned int* tbl_inuse;     // [n_tables]
   unsigned int* tbl_count;     // [n_tables] distinct keys inserted
   unsigned int* node_tbl;      // [M] 0 none, 1 being acquired, else table index + 2
   unsigned int* node_done;     // [M] chunks completed
-  int n_ids;                   // dense id space (identity hashing when the table covers it)
+  int n_ids;                   // label space (identity hashing when the table covers it)
+  unsigned long long* prof;    // optional [gridDim.x * 8] phase cycle counters (PPRB200_PROF=1)
 };
 
 struct ParShared {
-  int count;            // occupied slots of the shared table
-  int spilled;          // some entry went to the global table
+  int tcount;           // occupied slots of the tail table
+  int spilled;          // an entry found the tail table closed and no global table was bound
   int table;            // global table index of the current node (-1 none)
   unsigned int gmask;
   int gidentity;
   int is_last;
   int out_pos;
+  int ncand;
   unsigned int item;
-  unsigned long long red_a[16], red_b[16];
-  unsigned long long sel_prefix;
+  unsigned long long red_a[16];
   int sel_digit, sel_above, sel_cnt;
   unsigned int hist[256];
 };
@@ -191,61 +188,81 @@ __device__ __forceinline__ int gtable_find(const GSlot* slots, unsigned int mask
   }
 }
 
-template <int PAR_CAP, int PAR_THREADS>
-__global__ void __launch_bounds__(PAR_THREADS) merge_par_kernel(ParParams P) {
-  constexpr int PAR_LIMIT = PAR_CAP * 13 / 16 - PAR_THREADS;
+__device__ __forceinline__ void fixed_add_shared(uint2* word, unsigned long long x) {
+  const unsigned int xlo = (unsigned int)x, xhi = (unsigned int)(x >> 32);
+  const unsigned int old = atomicAdd(&word->x, xlo);
+  const unsigned int hi = xhi + ((old + xlo) < old ? 1u : 0u);
+  if (hi) atomicAdd(&word->y, hi);
+}
+
+template <int H, int TCAP>
+constexpr size_t par_smem_bytes() {
+  return (size_t)H * 8 + (size_t)TCAP * 14 + (size_t)H / 8 + sizeof(ParShared);
+}
+
+// H dense labels, TCAP tail slots, THREADS threads. TLIMIT distinct tail keys are admitted (concurrent inserts
+// may overshoot by < THREADS).
+template <int H, int TCAP, int THREADS>
+__global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
+  constexpr int TLIMIT = TCAP * 13 / 16 - THREADS;
+  constexpr int NW = THREADS / 32;
   extern __shared__ __align__(16) unsigned char smem[];
   const MergeParams& M = P.M;
   RunState* st = M.st;
   if (!st->active) return;
-  int* s_keys = reinterpret_cast<int*>(smem);
-  uint2* s_acc = reinterpret_cast<uint2*>(smem + (size_t)PAR_CAP * 4);
-  unsigned short* s_list = reinterpret_cast<unsigned short*>(smem + (size_t)PAR_CAP * 12);
-  ParShared* S = reinterpret_cast<ParShared*>(smem + (size_t)PAR_CAP * 14);
+  uint2* s_dense = reinterpret_cast<uint2*>(smem);
+  uint2* t_acc = reinterpret_cast<uint2*>(smem + (size_t)H * 8);
+  int* t_keys = reinterpret_cast<int*>(smem + (size_t)H * 8 + (size_t)TCAP * 8);
+  unsigned short* t_list = reinterpret_cast<unsigned short*>(smem + (size_t)H * 8 + (size_t)TCAP * 12);
+  unsigned int* s_zbits = reinterpret_cast<unsigned int*>(smem + (size_t)H * 8 + (size_t)TCAP * 14);  // touched with a 0 word
+  ParShared* S = reinterpret_cast<ParShared*>(smem + (size_t)H * 8 + (size_t)TCAP * 14 + (size_t)H / 8);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  constexpr int NW = PAR_THREADS / 32;
   const int Lp = M.Lp, groups = Lp >> 2, L = M.L;
   const bool init_mode = M.init_mode != 0;
   const double scale = (M.mode == MODE_GRANK) ? GRANK_HUB_SCALE : MC_HUB_SCALE;
   const double inv = (M.mode == MODE_GRANK) ? GRANK_HUB_INV : MC_HUB_INV;
+  const int* __restrict__ dense_of = M.g.dense_of;
 
-  for (int i = tid; i < PAR_CAP; i += PAR_THREADS) { s_keys[i] = KEY_EMPTY; s_acc[i] = make_uint2(0u, 0u); }
-  if (tid == 0) { S->count = 0; S->spilled = 0; S->table = -1; }
+  for (int i = tid; i < H; i += THREADS) s_dense[i] = make_uint2(0u, 0u);
+  for (int i = tid; i < H / 32; i += THREADS) s_zbits[i] = 0u;
+  for (int i = tid; i < TCAP; i += THREADS) { t_keys[i] = KEY_EMPTY; t_acc[i] = make_uint2(0u, 0u); }
+  if (tid == 0) { S->tcount = 0; S->spilled = 0; S->table = -1; }
   __syncthreads();
 
   int read_slot[2];
   read_slot[0] = st->slot[0];
   read_slot[1] = st->slot[1];
 
-  unsigned long long s_merged = 0, s_edges = 0, s_cands = 0, s_truncs = 0, s_ties = 0, s_bytes = 0, s_nodes = 0;
+  unsigned long long s_merged = 0, s_edges = 0, s_cands = 0, s_truncs = 0, s_ties = 0, s_bytes = 0, s_nodes = 0, s_requeue = 0;
 
-  // shared-table accumulate; returns false when the key is absent and the table is closed (caller spills)
-  auto smem_add = [&](int k, unsigned long long x) -> bool {
-    unsigned int h = hash_key(k) & (PAR_CAP - 1);
-    volatile int* keys = s_keys;
+  // tail-table accumulate; false when the key is absent and the table is closed (caller spills)
+  auto tail_add = [&](int k, unsigned long long x) -> bool {
+    unsigned int h = hash_key(k) & (TCAP - 1);
+    volatile int* keys = t_keys;
     for (;;) {
       const int cur = keys[h];
       if (cur == k) break;
       if (cur == KEY_EMPTY) {
-        if (*reinterpret_cast<volatile int*>(&S->count) >= PAR_LIMIT) return false;
-        const int old = atomicCAS(&s_keys[h], KEY_EMPTY, k);
-        if (old == KEY_EMPTY) { const int pos = atomicAdd(&S->count, 1); s_list[pos] = (unsigned short)h; break; }
+        if (*reinterpret_cast<volatile int*>(&S->tcount) >= TLIMIT) return false;
+        const int old = atomicCAS(&t_keys[h], KEY_EMPTY, k);
+        if (old == KEY_EMPTY) { const int pos = atomicAdd(&S->tcount, 1); t_list[pos] = (unsigned short)h; break; }
         if (old == k) break;
       }
-      h = (h + 1) & (PAR_CAP - 1);
+      h = (h + 1) & (TCAP - 1);
     }
-    const unsigned int xlo = (unsigned int)x, xhi = (unsigned int)(x >> 32);
-    const unsigned int old = atomicAdd(&s_acc[h].x, xlo);
-    const unsigned int carry = (old + xlo) < old ? 1u : 0u;
-    if (xhi + carry) atomicAdd(&s_acc[h].y, xhi + carry);
+    if (x) fixed_add_shared(&t_acc[h], x);
     return true;
   };
 
+  unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long t_last = clock64();
+#define PROF_MARK(i) do { if (P.prof && tid == 0) { const long long t_now = clock64(); pc[i] += (unsigned long long)(t_now - t_last); t_last = t_now; } } while (0)
   for (;;) {
     if (tid == 0) S->item = atomicAdd(&st->work[P.work_idx], 1u);
     __syncthreads();
     const unsigned int item = S->item;
     if (item >= (unsigned)P.n_items) break;
+    PROF_MARK(0);
     const int p = P.item_pos[item];
     const long long cb = P.item_begin[item];
     const int clen = P.item_len[item];
@@ -255,6 +272,8 @@ __global__ void __launch_bounds__(PAR_THREADS) merge_par_kernel(ParParams P) {
     const int self_id = M.g.label[p];
     const double f = M.damping / (double)(unsigned long long)deg;
     const double mult = f;  // the hub path pre-scales by f = d/outdeg in both modes (oracle: llrint((x * f) * scale))
+    // (x * f) * 2^s == x * (f * 2^s) exactly: scaling by a power of two commutes with the rounding of the product
+    const double fscale = f * scale;
     const double self0 = (M.mode == MODE_GRANK) ? M.self_grank : 1.0;
     const int write_slot = init_mode ? st->slot[M.colour] : (st->slot[M.colour] ^ 1);
 
@@ -262,6 +281,8 @@ __global__ void __launch_bounds__(PAR_THREADS) merge_par_kernel(ParParams P) {
     GSlot* gslots = nullptr;
     unsigned int* glist = nullptr;
     unsigned int* gcount = nullptr;
+    double* cvals = nullptr;
+    int* cids = nullptr;
     auto bind_table = [&]() {
       if (tid == 0 && S->table < 0) {
         unsigned int v = atomicCAS(&P.node_tbl[p], 0u, 1u);
@@ -275,9 +296,9 @@ __global__ void __launch_bounds__(PAR_THREADS) merge_par_kernel(ParParams P) {
           while (v == 1u) v = atomicAdd(&P.node_tbl[p], 0u);
         }
         S->table = (int)v - 2;
-        // per-node capacity: never overflows (worst case deg*Lp+1 distinct keys, or the whole id space)
-        unsigned long long bound = (unsigned long long)deg * (unsigned long long)(init_mode ? 1 : Lp) + 2ull;
-        unsigned long long want = 2ull * bound;
+        // per-node capacity: never overflows (worst case deg*Lp+1 distinct keys, or the whole label space)
+        const unsigned long long bound = (unsigned long long)deg * (unsigned long long)(init_mode ? 1 : Lp) + 2ull;
+        const unsigned long long want = 2ull * bound;
         unsigned int cap = P.capmax;
         if (want < (unsigned long long)P.capmax) { cap = 1024u; while ((unsigned long long)cap < want) cap <<= 1; }
         S->gmask = cap - 1u;
@@ -287,26 +308,39 @@ __global__ void __launch_bounds__(PAR_THREADS) merge_par_kernel(ParParams P) {
       unsigned char* base = P.pool + (size_t)S->table * P.tbl_bytes;
       gslots = reinterpret_cast<GSlot*>(base);
       glist = reinterpret_cast<unsigned int*>(base + (size_t)P.capmax * sizeof(GSlot));
+      cvals = reinterpret_cast<double*>(base + (size_t)P.capmax * (sizeof(GSlot) + 4));
+      cids = reinterpret_cast<int*>(base + (size_t)P.capmax * (sizeof(GSlot) + 4 + 4));
       gcount = &P.tbl_count[S->table];
     };
     if (nchunks > 1) bind_table();
 
-    if (tid == 0 && cb == rb) {  // first chunk owns the self term (grank.h:101 / mccompletepathv2.h:226)
-      const unsigned long long x = init_mode ? 0ull : (unsigned long long)__double2ll_rn(self0 * scale);
-      const unsigned int h = hash_key(self_id) & (PAR_CAP - 1);
-      s_keys[h] = self_id;
-      s_acc[h] = make_uint2((unsigned int)x, (unsigned int)(x >> 32));
-      s_list[0] = (unsigned short)h;
-      S->count = 1;
-    }
+    auto put_self = [&]() {  // first chunk owns the self term (grank.h:101 / mccompletepathv2.h:226)
+      if (tid == 0 && cb == rb) {
+        const unsigned long long x = init_mode ? 0ull : (unsigned long long)__double2ll_rn(self0 * scale);
+        if ((unsigned)self_id < (unsigned)H) {
+          if (x) s_dense[self_id] = make_uint2((unsigned int)x, (unsigned int)(x >> 32));
+          else s_zbits[self_id >> 5] |= 1u << (self_id & 31);
+        } else {
+          const unsigned int h = hash_key(self_id) & (TCAP - 1);
+          t_keys[h] = self_id;
+          t_acc[h] = make_uint2((unsigned int)x, (unsigned int)(x >> 32));
+          t_list[0] = (unsigned short)h;
+          S->tcount = 1;
+        }
+      }
+    };
+    put_self();
     __syncthreads();
 
-    // ---- accumulate: warp w takes runs of 32 successors of the chunk; a contribution whose key is absent
-    // from the (closed) shared table goes to the global table when one is bound, else the pass is repeated ----
+    // ---- accumulate ----
     unsigned long long merged = 0;
-    auto contribute = [&](int k, unsigned long long xf, bool spill_ok) {
-      if (!smem_add(k, xf)) {
-        if (spill_ok) gtable_add(gslots, glist, gcount, S->gmask, S->gidentity, k, xf);
+    auto slow_contribute = [&](int k, unsigned long long x, bool spill_ok) {
+      if ((unsigned)k < (unsigned)H) {  // dense label with a zero word: remember that it was touched
+        atomicOr(&s_zbits[k >> 5], 1u << (k & 31));
+        return;
+      }
+      if (!tail_add(k, x)) {
+        if (spill_ok) gtable_add(gslots, glist, gcount, S->gmask, S->gidentity, k, x);
         else S->spilled = 1;
       }
     };
@@ -314,85 +348,114 @@ __global__ void __launch_bounds__(PAR_THREADS) merge_par_kernel(ParParams P) {
       merged = 0;
       if (init_mode) {
         // grank.h:79-80: every occurrence of a successor adds `factor`; here: multiplicity += 1
-        for (int j = tid; j < clen; j += PAR_THREADS) {
+        for (int j = tid; j < clen; j += THREADS) {
           const uint32_t c = M.g.col[cb + j];
           const int k = (c & COL_SINK) ? (int)(c & ~COL_SINK) : M.g.label[c & COL_POS_MASK];
-          contribute(k, 1ull, spill_ok);
+          if ((unsigned)k < (unsigned)H) fixed_add_shared(&s_dense[k], 1ull);
+          else slow_contribute(k, 1ull, spill_ok);
           merged++;
         }
         return;
       }
-      for (int j = w; j < clen; j += NW) {  // warp w merges successors w, w+NW, ...
-        const uint32_t c = M.g.col[cb + j];
+      BasketFrag cur;
+      cur.id = make_int4(-1, -1, -1, -1);
+      cur.sa = cur.sb = make_double2(0.0, 0.0);
+      int j = w;
+      uint32_t c = (j < clen) ? M.g.col[cb + j] : 0u;
+      auto prefetch = [&](uint32_t cc, BasketFrag* fr) {
+        fr->id = make_int4(-1, -1, -1, -1);
+        fr->sa = fr->sb = make_double2(0.0, 0.0);
+        if (!(cc & COL_SINK) && lane < groups) {
+          const unsigned char* slot = M.buf[read_slot[(cc >> COL_COLOUR_SHIFT) & 1u]] + (size_t)(cc & COL_POS_MASK) * slot_bytes(Lp);
+          load_frag(slot, Lp, lane, fr);
+        }
+      };
+      if (j < clen) prefetch(c, &cur);
+      for (; j < clen; j += NW) {  // warp w merges successors w, w+NW, ... with the next basket already in flight
+        const uint32_t cn = (j + NW < clen) ? M.g.col[cb + j + NW] : 0u;
+        BasketFrag nxt;
+        nxt.id = make_int4(-1, -1, -1, -1);
+        nxt.sa = nxt.sb = make_double2(0.0, 0.0);
+        if (j + NW < clen) prefetch(cn, &nxt);
         if (c & COL_SINK) {
           if (lane == 0) {
+            const int k = (int)(c & ~COL_SINK);
             const double x = (M.mode == MODE_GRANK) ? M.self_grank : 1.0;
-            contribute((int)(c & ~COL_SINK), (unsigned long long)__double2ll_rn((x * mult) * scale), spill_ok);
+            const unsigned long long xf = (unsigned long long)__double2ll_rn(x * fscale);
+            if ((unsigned)k < (unsigned)H && xf) fixed_add_shared(&s_dense[k], xf);
+            else slow_contribute(k, xf, spill_ok);
             merged++;
           }
         } else {
-          const unsigned int sp = c & COL_POS_MASK;
-          const int sc = (int)((c >> COL_COLOUR_SHIFT) & 1u);
-          const unsigned char* slot = M.buf[read_slot[sc]] + (size_t)sp * slot_bytes(Lp);
+          const unsigned char* slot = M.buf[read_slot[(c >> COL_COLOUR_SHIFT) & 1u]] + (size_t)(c & COL_POS_MASK) * slot_bytes(Lp);
           for (int g = lane; g < groups; g += 32) {
             BasketFrag fr;
-            load_frag(slot, Lp, g, &fr);
+            if (g == lane) fr = cur; else load_frag(slot, Lp, g, &fr);
             const int ids[4] = {fr.id.x, fr.id.y, fr.id.z, fr.id.w};
             const double xs[4] = {fr.sa.x, fr.sa.y, fr.sb.x, fr.sb.y};
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-              if (ids[e] >= 0) {
-                contribute(ids[e], (unsigned long long)__double2ll_rn((xs[e] * mult) * scale), spill_ok);
-                merged++;
-              }
+              const int k = ids[e];
+              const unsigned long long xf = (unsigned long long)__double2ll_rn(xs[e] * fscale);
+              if ((unsigned)k < (unsigned)H && xf) fixed_add_shared(&s_dense[k], xf);   // hot path
+              else if (k >= 0) slow_contribute(k, xf, spill_ok);
+              merged += (k >= 0);
             }
           }
         }
+        cur = nxt;
+        c = cn;
       }
     };
-    // a node expected to outgrow the shared table binds its global table up front
-    if (S->table < 0 && M.ncand[p] > PAR_LIMIT - PAR_THREADS) bind_table();
+    // a node expected to outgrow the tail table binds its global table up front
+    if (S->table < 0 && M.ncand[p] > TLIMIT + H / 2) bind_table();
+    PROF_MARK(1);
     accumulate(S->table >= 0);
     __syncthreads();
+    PROF_MARK(2);
     if (S->spilled) {
       // mispredicted: drop the partial sums, bind a table and run the chunk again with spilling enabled
-      const int dirty = S->count;
       __syncthreads();
-      for (int i = tid; i < dirty; i += PAR_THREADS) {
-        const int s = s_list[i];
-        s_keys[s] = KEY_EMPTY;
-        s_acc[s] = make_uint2(0u, 0u);
+      for (int i = tid; i < H; i += THREADS) s_dense[i] = make_uint2(0u, 0u);
+      for (int i = tid; i < H / 32; i += THREADS) s_zbits[i] = 0u;
+      const int dirty = S->tcount;
+      for (int i = tid; i < dirty; i += THREADS) {
+        const int s = t_list[i];
+        t_keys[s] = KEY_EMPTY;
+        t_acc[s] = make_uint2(0u, 0u);
       }
       __syncthreads();
-      if (tid == 0) { S->count = 0; S->spilled = 0; }
+      if (tid == 0) { S->tcount = 0; S->spilled = 0; s_requeue++; }
       bind_table();
-      if (tid == 0 && cb == rb) {
-        const unsigned long long x = init_mode ? 0ull : (unsigned long long)__double2ll_rn(self0 * scale);
-        const unsigned int h = hash_key(self_id) & (PAR_CAP - 1);
-        s_keys[h] = self_id;
-        s_acc[h] = make_uint2((unsigned int)x, (unsigned int)(x >> 32));
-        s_list[0] = (unsigned short)h;
-        S->count = 1;
-      }
+      put_self();
       __syncthreads();
       accumulate(true);
       __syncthreads();
+      PROF_MARK(3);
     }
 
-    const int ns = S->count;  // occupied shared slots
+    const int nt = S->tcount;  // occupied tail slots
     const bool use_global = S->table >= 0;
-    int n = ns;
+    int n = 0;
     int kept = 0, old_cnt = 0;
     bool finalize = !use_global;  // single chunk, nothing spilled: finish from shared memory
     if (use_global) {
-      // flush the shared table into the node's global table
-      for (int i = tid; i < ns; i += PAR_THREADS) {
-        const int s = s_list[i];
-        const unsigned long long a = ((unsigned long long)s_acc[s].y << 32) | s_acc[s].x;
-        gtable_add(gslots, glist, gcount, S->gmask, S->gidentity, s_keys[s], a);
+      // flush the shared accumulators into the node's global table (and leave them clean)
+      for (int i = tid; i < H; i += THREADS) {
+        const uint2 a = s_dense[i];
+        const bool z = (s_zbits[i >> 5] >> (i & 31)) & 1u;
+        if ((a.x | a.y) || z) {
+          gtable_add(gslots, glist, gcount, S->gmask, S->gidentity, i, ((unsigned long long)a.y << 32) | a.x);
+          s_dense[i] = make_uint2(0u, 0u);
+        }
+      }
+      for (int i = tid; i < nt; i += THREADS) {
+        const int s = t_list[i];
+        gtable_add(gslots, glist, gcount, S->gmask, S->gidentity, t_keys[s], ((unsigned long long)t_acc[s].y << 32) | t_acc[s].x);
       }
       __threadfence();
       __syncthreads();
+      for (int i = tid; i < H / 32; i += THREADS) s_zbits[i] = 0u;
       if (tid == 0) {
         const unsigned int done = atomicAdd(&P.node_done[p], 1u) + 1u;
         S->is_last = done == (unsigned)nchunks;
@@ -400,18 +463,44 @@ __global__ void __launch_bounds__(PAR_THREADS) merge_par_kernel(ParParams P) {
       }
       __syncthreads();
       finalize = S->is_last != 0;
-      if (finalize) n = (int)*reinterpret_cast<volatile unsigned int*>(gcount);
+      PROF_MARK(4);
     }
 
     if (finalize) {
       const double base_self = init_mode ? M.self_grank : 0.0;
-      // candidate accessors
-      auto cand_id = [&](int i) -> int { return use_global ? gslots[glist[i]].key : s_keys[s_list[i]]; };
+      // candidates: a virtual index space. shared: [0,H) dense labels (pred: touched), [H, H+nt) tail list;
+      // global: compact arrays gathered once from the table.
+      int nv;
+      if (use_global) {
+        n = (int)*reinterpret_cast<volatile unsigned int*>(gcount);
+        nv = n;
+        for (int i = tid; i < n; i += THREADS) {
+          const GSlot g = gslots[glist[i]];
+          cids[i] = g.key;
+          cvals[i] = par_score(g.acc, init_mode, inv, mult, (init_mode && g.key == self_id) ? base_self : 0.0);
+        }
+        __syncthreads();
+      } else {
+        nv = H + nt;
+        int c = 0;
+        for (int i = tid; i < H; i += THREADS) {
+          const uint2 a = s_dense[i];
+          c += ((a.x | a.y) != 0u) || ((s_zbits[i >> 5] >> (i & 31)) & 1u);
+        }
+        n = (int)block_reduce_sum_ll(c, S->red_a) + nt;
+      }
+      auto cand_ok = [&](int i) -> bool {
+        if (use_global || i >= H) return true;
+        const uint2 a = s_dense[i];
+        return ((a.x | a.y) != 0u) || ((s_zbits[i >> 5] >> (i & 31)) & 1u);
+      };
+      auto cand_id = [&](int i) -> int { return use_global ? cids[i] : (i < H ? i : t_keys[t_list[i - H]]); };
       auto cand_val = [&](int i) -> double {
+        if (use_global) return cvals[i];
         unsigned long long a;
         int id;
-        if (use_global) { const GSlot g = gslots[glist[i]]; a = g.acc; id = g.key; }
-        else { const int s = s_list[i]; a = ((unsigned long long)s_acc[s].y << 32) | s_acc[s].x; id = s_keys[s]; }
+        if (i < H) { a = ((unsigned long long)s_dense[i].y << 32) | s_dense[i].x; id = i; }
+        else { const int s = t_list[i - H]; a = ((unsigned long long)t_acc[s].y << 32) | t_acc[s].x; id = t_keys[s]; }
         return par_score(a, init_mode, inv, mult, (init_mode && id == self_id) ? base_self : 0.0);
       };
       Threshold th;
@@ -423,20 +512,23 @@ __global__ void __launch_bounds__(PAR_THREADS) merge_par_kernel(ParParams P) {
         bool tie;
         int krem;
         auto keyfn = [&](int i) { return (unsigned long long)__double_as_longlong(cand_val(i)); };
-        auto all = [&](int) { return true; };
-        th.bits = block_radix_select(n, L, keyfn, all, S, &tie, &krem);
+        th.bits = block_radix_select(nv, L, keyfn, cand_ok, S, &tie, &krem);
         if (tie) {
           const unsigned long long tb = th.bits;
-          auto idkey = [&](int i) { return (unsigned long long)(0x7fffffff - cand_id(i)); };
-          auto tied = [&](int i) { return (unsigned long long)__double_as_longlong(cand_val(i)) == tb; };
+          auto idkey = [&](int i) { return (unsigned long long)(0x7fffffff - dense_of[cand_id(i)]); };
+          auto tied = [&](int i) { return cand_ok(i) && (unsigned long long)__double_as_longlong(cand_val(i)) == tb; };
           bool tie2;
           int krem2;
-          const unsigned long long tid_key = block_radix_select(n, krem, idkey, tied, S, &tie2, &krem2);
+          const unsigned long long tid_key = block_radix_select(nv, krem, idkey, tied, S, &tie2, &krem2);
           th.id_max = 0x7fffffff - (int)tid_key;
           s_ties += (tid == 0);
         }
         s_truncs += (tid == 0);
       }
+      auto selected = [&](unsigned long long bits, int label) -> bool {
+        return bits > th.bits || (bits == th.bits && (th.id_max == 0x7fffffff || dense_of[label] <= th.id_max));
+      };
+      PROF_MARK(5);
       // ---- write B'_v ----
       unsigned char* out = M.buf[write_slot] + (size_t)p * slot_bytes(Lp);
       int* out_ids = reinterpret_cast<int*>(out);
@@ -444,21 +536,22 @@ __global__ void __launch_bounds__(PAR_THREADS) merge_par_kernel(ParParams P) {
       if (tid == 0) S->out_pos = 0;
       __syncthreads();
       long long dsum = 0;
-      for (int i = tid; i < n; i += PAR_THREADS) {
+      for (int i = tid; i < nv; i += THREADS) {
+        if (!cand_ok(i)) continue;
         const int id = cand_id(i);
         const double v = cand_val(i);
-        if (is_selected(th, (unsigned long long)__double_as_longlong(v), id)) {
+        if (selected((unsigned long long)__double_as_longlong(v), id)) {
           const int pos = atomicAdd(&S->out_pos, 1);
           out_ids[pos] = id;
           out_sc[score_index(pos, Lp)] = v;  // hub path: no post-scale (already multiplied by f)
           dsum += fix_norm(v);
         }
       }
-      for (int i = kept + tid; i < Lp; i += PAR_THREADS) out_ids[i] = KEY_EMPTY;
+      for (int i = kept + tid; i < Lp; i += THREADS) out_ids[i] = KEY_EMPTY;
       // ---- norm1 against the old basket (pprInternal.h:147-165) ----
       if (M.do_norm) {
         const unsigned char* old = M.buf[write_slot ^ 1] + (size_t)p * slot_bytes(Lp);
-        for (int g = tid; g < groups; g += PAR_THREADS) {
+        for (int g = tid; g < groups; g += THREADS) {
           BasketFrag fr;
           load_frag(old, Lp, g, &fr);
           const int ids[4] = {fr.id.x, fr.id.y, fr.id.z, fr.id.w};
@@ -468,19 +561,23 @@ __global__ void __launch_bounds__(PAR_THREADS) merge_par_kernel(ParParams P) {
             if (ids[e] >= 0) {
               old_cnt++;
               bool found = false;
-              double nv = 0.0;
+              double nv_ = 0.0;
               if (use_global) {
                 const int s = gtable_find(gslots, S->gmask, S->gidentity, ids[e]);
-                if (s >= 0) { found = true; nv = par_score(gslots[s].acc, false, inv, mult, 0.0); }
+                if (s >= 0) { found = true; nv_ = par_score(gslots[s].acc, false, inv, mult, 0.0); }
+              } else if ((unsigned)ids[e] < (unsigned)H) {
+                const uint2 a = s_dense[ids[e]];
+                found = ((a.x | a.y) != 0u) || ((s_zbits[ids[e] >> 5] >> (ids[e] & 31)) & 1u);
+                nv_ = par_score(((unsigned long long)a.y << 32) | a.x, false, inv, mult, 0.0);
               } else {
-                for (unsigned int h = hash_key(ids[e]) & (PAR_CAP - 1);; h = (h + 1) & (PAR_CAP - 1)) {
-                  const int cur = s_keys[h];
-                  if (cur == ids[e]) { found = true; nv = par_score(((unsigned long long)s_acc[h].y << 32) | s_acc[h].x, false, inv, mult, 0.0); break; }
+                for (unsigned int h = hash_key(ids[e]) & (TCAP - 1);; h = (h + 1) & (TCAP - 1)) {
+                  const int cur = t_keys[h];
+                  if (cur == ids[e]) { found = true; nv_ = par_score(((unsigned long long)t_acc[h].y << 32) | t_acc[h].x, false, inv, mult, 0.0); break; }
                   if (cur == KEY_EMPTY) break;
                 }
               }
-              const bool in_new = found && is_selected(th, (unsigned long long)__double_as_longlong(nv), ids[e]);
-              if (in_new) dsum += fix_norm(fabs(nv - xs[e])) - fix_norm(nv);
+              const bool in_new = found && selected((unsigned long long)__double_as_longlong(nv_), ids[e]);
+              if (in_new) dsum += fix_norm(fabs(nv_ - xs[e])) - fix_norm(nv_);
               else dsum += fix_norm(xs[e]);
             }
           }
@@ -492,7 +589,7 @@ __global__ void __launch_bounds__(PAR_THREADS) merge_par_kernel(ParParams P) {
       __syncthreads();
       if (use_global) {
         // leave the pool table clean and hand it back
-        for (int i = tid; i < n; i += PAR_THREADS) {
+        for (int i = tid; i < n; i += THREADS) {
           const unsigned int h = glist[i];
           gslots[h].key = KEY_EMPTY;
           gslots[h].acc = 0ull;
@@ -506,6 +603,9 @@ __global__ void __launch_bounds__(PAR_THREADS) merge_par_kernel(ParParams P) {
           __threadfence();
           atomicExch(&P.tbl_inuse[S->table], 0u);
         }
+      } else {
+        for (int i = tid; i < H; i += THREADS) s_dense[i] = make_uint2(0u, 0u);
+        for (int i = tid; i < H / 32; i += THREADS) s_zbits[i] = 0u;
       }
       if (tid == 0) {
         M.ncand[p] = n;
@@ -514,23 +614,27 @@ __global__ void __launch_bounds__(PAR_THREADS) merge_par_kernel(ParParams P) {
         s_bytes += 12ull * (unsigned long long)old_cnt + 12ull * (unsigned long long)kept + 4ull + 16ull;
       }
     }
-    // ---- reset the shared table through its list ----
-    for (int i = tid; i < ns; i += PAR_THREADS) {
-      const int s = s_list[i];
-      s_keys[s] = KEY_EMPTY;
-      s_acc[s] = make_uint2(0u, 0u);
+    PROF_MARK(6);
+    // ---- reset the tail table through its list ----
+    for (int i = tid; i < nt; i += THREADS) {
+      const int s = t_list[i];
+      t_keys[s] = KEY_EMPTY;
+      t_acc[s] = make_uint2(0u, 0u);
     }
     merged = (unsigned long long)block_reduce_sum_ll((long long)merged, S->red_a);
     if (tid == 0) {
       s_merged += merged;
       s_edges += (unsigned long long)clen;
       s_bytes += 12ull * merged + 4ull * (unsigned long long)clen;
-      S->count = 0;
+      S->tcount = 0;
       S->spilled = 0;
       S->table = -1;
     }
     __syncthreads();
+    PROF_MARK(7);
   }
+  if (P.prof && tid == 0)
+    for (int i = 0; i < 8; i++) atomicAdd(&P.prof[(size_t)blockIdx.x * 8 + i], pc[i]);
   if (tid == 0) {
     if (s_nodes) atomicAdd(&st->node_iters, s_nodes);
     if (s_edges) atomicAdd(&st->edge_reads, s_edges);
@@ -539,6 +643,7 @@ __global__ void __launch_bounds__(PAR_THREADS) merge_par_kernel(ParParams P) {
     if (s_truncs) atomicAdd(&st->truncs, s_truncs);
     if (s_ties) atomicAdd(&st->ties, s_ties);
     if (s_bytes) atomicAdd(&st->abytes, s_bytes);
+    if (s_requeue) atomicAdd(&st->requeues, s_requeue);
   }
 }
 

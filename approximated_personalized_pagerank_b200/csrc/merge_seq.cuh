@@ -208,7 +208,7 @@ __device__ bool merge_node_seq(const MergeParams& P, const WarpTable<IdxT>& T, u
     th.bits = warp_radix_select(n, L, keyfn, all, hist, &tie, &krem);
     if (tie) {
       const unsigned long long tb = th.bits;
-      auto idkey = [&](int i) { return (unsigned long long)(0x7fffffff - T.keys[T.list[i]]); };
+      auto idkey = [&](int i) { return (unsigned long long)(0x7fffffff - P.g.dense_of[T.keys[T.list[i]]]); };
       auto tied = [&](int i) { return (unsigned long long)__double_as_longlong(T.vals[T.list[i]]) == tb; };
       bool tie2;
       int krem2;
@@ -219,6 +219,10 @@ __device__ bool merge_node_seq(const MergeParams& P, const WarpTable<IdxT>& T, u
     st_truncs += (lane == 0);
   }
 
+  // ties are cut by dense id: only entries whose score equals the threshold need the label -> dense lookup
+  auto selected = [&](unsigned long long bits, int label) -> bool {
+    return bits > th.bits || (bits == th.bits && (th.id_max == 0x7fffffff || P.g.dense_of[label] <= th.id_max));
+  };
   // ---- write B'_v, norm1 vs B_v ----
   unsigned char* out = P.buf[write_slot] + (size_t)p * slot_bytes(Lp);
   int* out_ids = reinterpret_cast<int*>(out);
@@ -234,7 +238,7 @@ __device__ bool merge_node_seq(const MergeParams& P, const WarpTable<IdxT>& T, u
       const int s = T.list[i];
       id = T.keys[s];
       v = T.vals[s];
-      sel = is_selected(th, (unsigned long long)__double_as_longlong(v), id);
+      sel = selected((unsigned long long)__double_as_longlong(v), id);
     }
     const unsigned m = __ballot_sync(FULL, sel);
     if (sel) {
@@ -266,7 +270,7 @@ __device__ bool merge_node_seq(const MergeParams& P, const WarpTable<IdxT>& T, u
           double nv = 0.0;
           if (s >= 0) {
             nv = T.vals[s];
-            in_new = is_selected(th, (unsigned long long)__double_as_longlong(nv), ids[e]);
+            in_new = selected((unsigned long long)__double_as_longlong(nv), ids[e]);
           }
           if (in_new) dsum += fix_norm(fabs(nv - xs[e])) - fix_norm(nv);
           else dsum += fix_norm(xs[e]);

@@ -78,7 +78,8 @@ __global__ void iter_end_kernel(RunState* st, int colour, double tolerance) {
 
 // final keepTop(K) (grank.h:143-147, mccompletepathv2.h:252-256): one warp per dense id; output sorted
 // (score desc, id asc) by rank counting over the <= L basket entries.
-__global__ void final_topk_kernel(const int* __restrict__ pos_of, const unsigned char* __restrict__ colour,
+__global__ void final_topk_kernel(const int* __restrict__ pos_of, const int* __restrict__ dense_of,
+                                  const unsigned char* __restrict__ colour,
                                   unsigned char* buf0, unsigned char* buf1, const RunState* st, int n, int Lp, int K,
                                   double sink_score, int* __restrict__ out_ids, double* __restrict__ out_scores,
                                   unsigned int* __restrict__ out_cnt, unsigned long long* trunc_ties) {
@@ -104,7 +105,7 @@ __global__ void final_topk_kernel(const int* __restrict__ pos_of, const unsigned
     int cnt = 0;
     for (int e = lane; e < Lp; e += 32) {
       const int id = ids[e];
-      s_id[e] = id;
+      s_id[e] = id >= 0 ? dense_of[id] : -1;
       s_sc[e] = id >= 0 ? sc[score_index(e, Lp)] : 0.0;
       cnt += id >= 0;
     }
@@ -176,6 +177,7 @@ struct pprb200_session {
   unsigned int* d_node_tbl = nullptr;
   unsigned int* d_node_done = nullptr;
   int32_t max_deg_seq = 0, max_deg_par = 0;
+  unsigned long long* d_prof = nullptr;  // [2][sm_count*3][8] phase cycles of merge_par (debug, PPRB200_PROF=1)
   int32_t colour_count[2] = {0, 0};  // all nodes (sinks included) per colour
   int32_t max_deg = 0;
   // device
@@ -183,6 +185,7 @@ struct pprb200_session {
   uint32_t* d_col = nullptr;
   int* d_label = nullptr;
   int* d_pos_of = nullptr;
+  int* d_dense_of = nullptr;
   unsigned char* d_colour = nullptr;
   unsigned char* d_buf[2] = {nullptr, nullptr};
   size_t buf_bytes = 0;
@@ -231,13 +234,13 @@ static int dev_alloc(T** p, size_t count) {
 
 static void session_free(pprb200_session* s) {
   if (!s) return;
-  cudaFree(s->d_row_off); cudaFree(s->d_col); cudaFree(s->d_label); cudaFree(s->d_pos_of); cudaFree(s->d_colour);
+  cudaFree(s->d_row_off); cudaFree(s->d_col); cudaFree(s->d_label); cudaFree(s->d_pos_of); cudaFree(s->d_dense_of); cudaFree(s->d_colour);
   cudaFree(s->d_buf[0]); cudaFree(s->d_buf[1]);
   for (int i = 0; i < 3; i++) cudaFree(s->d_queue[i]);
   cudaFree(s->d_ncand); cudaFree(s->d_state); cudaFree(s->d_final_stats); cudaFree(s->d_ws);
   cudaFree(s->d_out_ids); cudaFree(s->d_out_scores); cudaFree(s->d_out_cnt);
   cudaFree(s->d_item_pos); cudaFree(s->d_item_off); cudaFree(s->d_item_len); cudaFree(s->d_pool);
-  cudaFree(s->d_tbl_inuse); cudaFree(s->d_tbl_count); cudaFree(s->d_node_tbl); cudaFree(s->d_node_done);
+  cudaFree(s->d_prof); cudaFree(s->d_tbl_inuse); cudaFree(s->d_tbl_count); cudaFree(s->d_node_tbl); cudaFree(s->d_node_done);
   if (s->ev_begin) cudaEventDestroy(s->ev_begin);
   if (s->ev_end) cudaEventDestroy(s->ev_end);
   for (auto e : s->ev_merge) cudaEventDestroy(e);
@@ -301,6 +304,15 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
     s->range_begin[c] = cls_begin[c][0];
     s->range_end[c] = cls_end[c][0];
   }
+  // rank labels: in-degree descending, ties by dense id (the keys stored in the baskets)
+  std::vector<int32_t> dense_of((size_t)n), rank_of((size_t)n);
+  {
+    std::vector<int64_t> indeg((size_t)n, 0);
+    for (int64_t i = 0; i < row_ptr[n]; i++) indeg[(size_t)col[i]]++;
+    std::iota(dense_of.begin(), dense_of.end(), 0);
+    std::stable_sort(dense_of.begin(), dense_of.end(), [&](int32_t x, int32_t y) { return indeg[x] > indeg[y]; });
+    for (int32_t r = 0; r < n; r++) rank_of[(size_t)dense_of[r]] = r;
+  }
   const int32_t M = (int32_t)order.size();
   s->M = M;
   std::vector<int32_t> pos_of((size_t)n, -1);
@@ -340,7 +352,7 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
     long long o = row_off[p];
     for (int64_t i = row_ptr[v]; i < row_ptr[v + 1]; i++) {
       const int32_t su = col[i];
-      enc[(size_t)o++] = pos_of[su] < 0 ? (COL_SINK | (uint32_t)su)
+      enc[(size_t)o++] = pos_of[su] < 0 ? (COL_SINK | (uint32_t)rank_of[su])
                                          : ((uint32_t)pos_of[su] | ((uint32_t)colour[su] << COL_COLOUR_SHIFT));
     }
   }
@@ -350,7 +362,7 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   const int Lp = roundup4((int)max_L);
   s->buf_bytes = (size_t)std::max(M, 1) * slot_bytes(Lp);
   if ((rc = dev_alloc(&s->d_row_off, (size_t)M + 1)) || (rc = dev_alloc(&s->d_col, (size_t)E)) ||
-      (rc = dev_alloc(&s->d_label, (size_t)M)) || (rc = dev_alloc(&s->d_pos_of, (size_t)n)) ||
+      (rc = dev_alloc(&s->d_label, (size_t)M)) || (rc = dev_alloc(&s->d_pos_of, (size_t)n)) || (rc = dev_alloc(&s->d_dense_of, (size_t)n)) ||
       (rc = dev_alloc(&s->d_colour, (size_t)n)) || (rc = dev_alloc(&s->d_buf[0], s->buf_bytes)) ||
       (rc = dev_alloc(&s->d_buf[1], s->buf_bytes)) || (rc = dev_alloc(&s->d_queue[0], (size_t)M)) ||
       (rc = dev_alloc(&s->d_queue[1], (size_t)M)) || (rc = dev_alloc(&s->d_queue[2], (size_t)M)) ||
@@ -367,7 +379,10 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   } while (0)
   UP(s->d_row_off, row_off.data(), ((size_t)M + 1) * sizeof(long long));
   if (E) UP(s->d_col, enc.data(), (size_t)E * sizeof(uint32_t));
-  if (M) UP(s->d_label, order.data(), (size_t)M * sizeof(int));
+  std::vector<int32_t> label((size_t)std::max(M, 1));
+  for (int32_t p = 0; p < M; p++) label[p] = rank_of[order[p]];
+  if (M) UP(s->d_label, label.data(), (size_t)M * sizeof(int));
+  if (n) UP(s->d_dense_of, dense_of.data(), (size_t)n * sizeof(int));
   if (n) UP(s->d_pos_of, pos_of.data(), (size_t)n * sizeof(int));
   if (n) UP(s->d_colour, colour.data(), (size_t)n);
   if (s->n_items > 0) {
@@ -378,7 +393,7 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
     while ((unsigned long long)cap < worst) cap <<= 1;
     s->capmax = cap;
     s->n_tables = s->sm_count * 3 + 8;  // >= CTAs in flight of either merge_par instantiation
-    s->tbl_bytes = (size_t)cap * (sizeof(GSlot) + sizeof(unsigned int));
+    s->tbl_bytes = (size_t)cap * (sizeof(GSlot) + sizeof(unsigned int) + 4 + 2);  // slots, slot list, compact scores (cap/2 x 8), labels (cap/2 x 4)
     if ((rc = dev_alloc(&s->d_item_pos, (size_t)s->n_items)) || (rc = dev_alloc(&s->d_item_off, (size_t)s->n_items)) ||
         (rc = dev_alloc(&s->d_item_len, (size_t)s->n_items)) || (rc = dev_alloc(&s->d_pool, s->tbl_bytes * (size_t)s->n_tables)) ||
         (rc = dev_alloc(&s->d_tbl_inuse, (size_t)s->n_tables)) || (rc = dev_alloc(&s->d_tbl_count, (size_t)s->n_tables)) ||
@@ -406,6 +421,10 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   cudaMemsetAsync(s->d_ncand, 0, (size_t)std::max(M, 1) * sizeof(int), st);
   cudaEventCreate(&s->ev_begin);
   cudaEventCreate(&s->ev_end);
+  if (getenv("PPRB200_PROF")) {
+    if ((rc = dev_alloc(&s->d_prof, (size_t)2 * s->sm_count * 3 * 8))) { session_free(s); return rc; }
+    cudaMemsetAsync(s->d_prof, 0, (size_t)2 * s->sm_count * 3 * 8 * sizeof(unsigned long long), st);
+  }
   s->h2d_ms = now_ms() - t1;
   *out = s;
   return PPRB200_OK;
@@ -502,16 +521,16 @@ static int enqueue_cascade(pprb200_session* s, MergeParams P, int range_begin, i
   return PPRB200_OK;
 }
 
-template <int CAP, int THREADS>
+template <int H, int TCAP, int THREADS>
 static cudaError_t launch_par(pprb200_session* s, const ParParams& P, int grid) {
-  const size_t smem = (size_t)CAP * 14 + sizeof(ParShared);
+  const size_t smem = par_smem_bytes<H, TCAP>();
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(merge_par_kernel<CAP, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(merge_par_kernel<H, TCAP, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  merge_par_kernel<CAP, THREADS><<<grid, THREADS, smem, s->stream>>>(P);
+  merge_par_kernel<H, TCAP, THREADS><<<grid, THREADS, smem, s->stream>>>(P);
   s->launch_count++;
   return cudaGetLastError();
 }
@@ -543,8 +562,9 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
     P.item_len = s->d_item_len + b;
     P.n_items = e - b;
     P.work_idx = 4 + cls;
-    cudaError_t err = cls == 1 ? launch_par<16384, 512>(s, P, std::min(s->sm_count, e - b))
-                               : launch_par<4096, 128>(s, P, std::min(s->sm_count * 3, e - b));
+    P.prof = s->d_prof ? s->d_prof + (size_t)cls * s->sm_count * 3 * 8 : nullptr;
+    cudaError_t err = cls == 1 ? launch_par<12288, 8192, 512>(s, P, std::min(s->sm_count, e - b))
+                               : launch_par<2048, 4096, 128>(s, P, std::min(s->sm_count * 3, e - b));
     if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_par launch failed: %s", cudaGetErrorString(err));
   }
   return PPRB200_OK;
@@ -575,7 +595,7 @@ static int enqueue_final(pprb200_session* s, int L, uint32_t K, double sink_scor
   }
   cudaMemsetAsync(s->d_final_stats, 0, 2 * sizeof(unsigned long long), s->stream);
   const int grid = std::max(1, std::min((s->n + warps - 1) / warps, s->sm_count * 8));
-  final_topk_kernel<<<grid, warps * 32, smem, s->stream>>>(s->d_pos_of, s->d_colour, s->d_buf[0], s->d_buf[1], s->d_state,
+  final_topk_kernel<<<grid, warps * 32, smem, s->stream>>>(s->d_pos_of, s->d_dense_of, s->d_colour, s->d_buf[0], s->d_buf[1], s->d_state,
                                                            s->n, Lp, (int)K, sink_score, s->d_out_ids, s->d_out_scores,
                                                            s->d_out_cnt, s->d_final_stats);
   s->launch_count++;
@@ -611,7 +631,7 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
   s->launch_count = 1;
   MergeParams P;
   std::memset(&P, 0, sizeof(P));
-  P.g.row_off = s->d_row_off; P.g.col = s->d_col; P.g.label = s->d_label;
+  P.g.row_off = s->d_row_off; P.g.col = s->d_col; P.g.label = s->d_label; P.g.dense_of = s->d_dense_of;
   P.buf[0] = s->d_buf[0]; P.buf[1] = s->d_buf[1];
   P.st = s->d_state;
   P.mode = MODE_GRANK;
@@ -764,6 +784,17 @@ int pprb200_session_kernel_time(pprb200_session* s, int which, uint32_t* launche
   }
   if (launches) *launches = cnt;
   if (total_ms) *total_ms = tot;
+  return PPRB200_OK;
+}
+
+// debug: copy the merge_par phase cycle counters (PPRB200_PROF=1) and clear them; out[2 * sm*3 * 8]
+int pprb200_debug_prof(pprb200_session* s, unsigned long long* out, int* n_ctas) {
+  if (!s || !s->d_prof) return fail(PPRB200_ERR_STATE, "profiling counters not enabled (PPRB200_PROF=1)");
+  cudaStreamSynchronize(s->stream);
+  const size_t cnt = (size_t)2 * s->sm_count * 3 * 8;
+  cudaMemcpy(out, s->d_prof, cnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemset(s->d_prof, 0, cnt * sizeof(unsigned long long));
+  if (n_ctas) *n_ctas = s->sm_count * 3;
   return PPRB200_OK;
 }
 
