@@ -36,6 +36,7 @@ class Stats(C.Structure):
         ("walk_steps", C.c_uint64),
         ("walks", C.c_uint64),
         ("overflow_requeues", C.c_uint64),
+        ("walk_algorithmic_bytes", C.c_uint64),
         ("max_diff", C.c_double * 2),
         ("prep_ms", C.c_double),
         ("h2d_ms", C.c_double),

@@ -43,7 +43,7 @@ struct RunState {
   unsigned int work[8];      // work-fetch counters, one per kernel stage
   unsigned int qcount[4];    // overflow queue lengths (nodes that need a larger table)
   unsigned long long node_iters, edge_reads, merged, cands, truncs, ties, abytes, requeues;
-  unsigned long long walk_steps, walks;
+  unsigned long long walk_steps, walks, walk_bytes;
   unsigned int ws_next;      // bump allocator for the global-table workspace
   unsigned int pad;
 };

@@ -1,0 +1,231 @@
+// mc_walk.cuh -- the Monte-Carlo "complete path" walk phase (M0) of MCCompletePathV2.
+//
+// Reproduces include/mccompletepathv2.h:115-165 (walkNode) for every non-sink source with the north-star changes
+// (SURVEY.md 8a-12/13): the successor of each hop is drawn uniformly from a counter-based generator instead of the
+// reference's shared rotating index, every visit is counted exactly (no first-come cap) and the top-L is taken
+// afterwards. One thread per walk: Philox4x32-10 keyed (source dense id, walk index), counter = (hop/2, 0, seed);
+// hop parity picks words (0,1) or (2,3): word A chooses the successor (mulhi(A, outdeg)), word B is the teleport
+// coin (continue iff B < floor(d * 2^32)). The first edge is always taken, W = (size_t)(R * d) walks per source,
+// counts are divided by R (:132,:142-160). oracle/ppr_oracle.c:mc_walk_source is the CPU twin, bit for bit:
+// visit counts are integers, so neither the thread that ran a walk nor the GPU that ran a source matters.
+//
+// A CTA owns one source at a time: visit counts live in a shared-memory open-addressing table keyed by the CSR
+// column word of the visited node (position | colour, or sink | label -- unique per node); threads fetch walk
+// indices from a shared counter so that long walks do not idle the rest of the warp for long. A source whose set of
+// visited nodes outgrows the table is queued for the fallback instantiation (table in a global workspace).
+#pragma once
+#include "merge_par.cuh"
+
+namespace pprb200 {
+
+constexpr unsigned int MC_MAX_STEPS = 4096u;  // hard cap per walk (oracle: same); P[len > 4096] = d^4096
+constexpr uint32_t WALK_EMPTY = 0xffffffffu;  // never a valid column word (sink | label 0x7fffffff is out of range)
+
+struct WalkParams {
+  GraphDev g;
+  unsigned char* buf[2];
+  RunState* st;
+  int M;                      // sources = non-sink storage positions 0..M-1 (this rank: [src_begin, src_end))
+  int src_begin, src_end;
+  const unsigned char* colour;  // [n] colour by dense id (a node's own column word carries it)
+  int Lp, L;
+  unsigned int R;
+  unsigned long long W;
+  uint32_t thresh;
+  unsigned long long seed;
+  unsigned int tcap;          // table slots (power of two)
+  unsigned int limit;         // max distinct visited nodes admitted by this launch
+  int work_idx;
+  const unsigned int* queue_in;
+  int queue_in_idx;           // -1: the range [src_begin, src_end)
+  unsigned int* queue_out;    // nullable (fallback launch never overflows)
+  int queue_out_idx;
+  unsigned long long* ws;     // fallback: gridDim.x tables of tcap 64-bit slots
+};
+
+struct WalkSlot {
+  uint32_t key;
+  uint32_t count;
+};
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ uint32_t hash_word(uint32_t w) {
+  uint32_t x = w * 0x9E3779B1u;
+  return x ^ (x >> 15);
+}
+
+struct WalkShared {
+  ParShared P;               // scratch of block_radix_select
+  unsigned int next_walk;
+  unsigned int ndistinct;
+  int overflow;
+  unsigned int item;
+};
+
+template <bool GLOBAL, int THREADS>
+__global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  RunState* st = P.st;
+  WalkShared* S = reinterpret_cast<WalkShared*>(smem);
+  WalkSlot* tbl = GLOBAL ? reinterpret_cast<WalkSlot*>(P.ws + (size_t)blockIdx.x * P.tcap)
+                         : reinterpret_cast<WalkSlot*>(smem + ((sizeof(WalkShared) + 15) & ~(size_t)15));
+  const int tid = threadIdx.x;
+  const unsigned int mask = P.tcap - 1u;
+  const int Lp = P.Lp, L = P.L;
+  const double inv_r_den = (double)P.R;
+
+  unsigned int total;
+  if (P.queue_in_idx >= 0) total = st->qcount[P.queue_in_idx];
+  else total = (unsigned int)(P.src_end - P.src_begin);
+  const int write_slot = st->slot[0];
+  unsigned long long tot_steps = 0, tot_walks = 0, tot_bytes = 0, tot_truncs = 0, tot_ties = 0, tot_requeue = 0;
+
+  for (;;) {
+    if (tid == 0) S->item = atomicAdd(&st->work[P.work_idx], 1u);
+    __syncthreads();
+    const unsigned int item = S->item;
+    if (item >= total) break;
+    const int p = (P.queue_in_idx >= 0) ? (int)P.queue_in[item] : P.src_begin + (int)item;
+    const int self_label = P.g.label[p];
+    const uint32_t src_dense = (uint32_t)P.g.dense_of[self_label];
+    const uint32_t self_word = (uint32_t)p | ((uint32_t)P.colour[src_dense] << COL_COLOUR_SHIFT);
+
+    for (unsigned int i = tid; i < P.tcap; i += THREADS) { tbl[i].key = WALK_EMPTY; tbl[i].count = 0u; }
+    if (tid == 0) { S->next_walk = 0u; S->ndistinct = 1u; S->overflow = 0; }
+    __syncthreads();
+    if (tid == 0) {  // res[src] = R (mccompletepathv2.h:124)
+      const unsigned int h = hash_word(self_word) & mask;
+      tbl[h].key = self_word;
+      tbl[h].count = P.R;
+    }
+    __syncthreads();
+
+    // ---- walks ----
+    unsigned long long steps = 0;
+    for (;;) {
+      const unsigned int w = atomicAdd(&S->next_walk, 1u);
+      if ((unsigned long long)w >= P.W) break;
+      if (*reinterpret_cast<volatile int*>(&S->overflow)) break;
+      uint32_t pos = (uint32_t)p;
+      uint32_t rnd[4];
+      for (unsigned int step = 0; step < MC_MAX_STEPS; step++) {
+        const long long rb = P.g.row_off[pos], re = P.g.row_off[pos + 1];
+        if ((step & 1u) == 0u)
+          philox4x32_10(step >> 1, 0u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), src_dense, w, rnd);
+        const uint32_t a = rnd[(step & 1u) * 2u], c = rnd[(step & 1u) * 2u + 1u];
+        const unsigned long long deg = (unsigned long long)(re - rb);
+        const uint32_t word = P.g.col[rb + (long long)(((unsigned long long)a * deg) >> 32)];  // :149, random successor
+        // count the visit (:152-153 without the cap)
+        unsigned int h = hash_word(word) & mask;
+        for (;;) {
+          const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&tbl[h].key);
+          if (cur == word) break;
+          if (cur == WALK_EMPTY) {
+            const uint32_t old = atomicCAS(&tbl[h].key, WALK_EMPTY, word);
+            if (old == WALK_EMPTY) {
+              if (atomicAdd(&S->ndistinct, 1u) + 1u > P.limit) S->overflow = 1;
+              break;
+            }
+            if (old == word) break;
+          }
+          h = (h + 1u) & mask;
+        }
+        atomicAdd(&tbl[h].count, 1u);
+        steps++;
+        if (word & COL_SINK) break;   // :144-145 the walk stops on reaching a sink
+        if (!(c < P.thresh)) break;   // :155
+        if (*reinterpret_cast<volatile int*>(&S->overflow)) break;
+        pos = word & COL_POS_MASK;
+      }
+    }
+    __syncthreads();
+    if (S->overflow) {
+      if (tid == 0) {
+        const unsigned int q = atomicAdd(&st->qcount[P.queue_out_idx], 1u);
+        P.queue_out[q] = (unsigned int)p;
+        tot_requeue++;
+      }
+      __syncthreads();
+      continue;
+    }
+
+    // ---- top-L on (count desc, dense id asc), scores = count / R (:159-160) ----
+    const int n = (int)S->ndistinct;
+    auto word_label = [&](uint32_t wd) -> int { return (wd & COL_SINK) ? (int)(wd & ~COL_SINK) : P.g.label[wd & COL_POS_MASK]; };
+    Threshold th;
+    th.bits = 0ull;
+    th.id_max = 0x7fffffff;
+    int kept = n;
+    if (n > L) {
+      kept = L;
+      bool tie;
+      int krem;
+      auto occupied = [&](int i) { return tbl[i].key != WALK_EMPTY; };
+      auto keyfn = [&](int i) { return (unsigned long long)tbl[i].count; };
+      th.bits = block_radix_select((int)P.tcap, L, keyfn, occupied, &S->P, &tie, &krem);
+      if (tie) {
+        const unsigned long long tb = th.bits;
+        auto idkey = [&](int i) { return (unsigned long long)(0x7fffffff - P.g.dense_of[word_label(tbl[i].key)]); };
+        auto tied = [&](int i) { return tbl[i].key != WALK_EMPTY && (unsigned long long)tbl[i].count == tb; };
+        bool tie2;
+        int krem2;
+        const unsigned long long tid_key = block_radix_select((int)P.tcap, krem, idkey, tied, &S->P, &tie2, &krem2);
+        th.id_max = 0x7fffffff - (int)tid_key;
+        tot_ties += (tid == 0);
+      }
+      tot_truncs += (tid == 0);
+    }
+    unsigned char* out = P.buf[write_slot] + (size_t)p * slot_bytes(Lp);
+    int* out_ids = reinterpret_cast<int*>(out);
+    double* out_sc = reinterpret_cast<double*>(out + (size_t)Lp * 4);
+    if (tid == 0) S->P.out_pos = 0;
+    __syncthreads();
+    for (unsigned int i = tid; i < P.tcap; i += THREADS) {
+      const uint32_t wd = tbl[i].key;
+      if (wd == WALK_EMPTY) continue;
+      const unsigned long long cnt = tbl[i].count;
+      bool sel = cnt > th.bits;
+      int label = -1;
+      if (!sel && cnt == th.bits) {
+        label = word_label(wd);
+        sel = th.id_max == 0x7fffffff || P.g.dense_of[label] <= th.id_max;
+      }
+      if (sel) {
+        if (label < 0) label = word_label(wd);
+        const int pos = atomicAdd(&S->P.out_pos, 1);
+        out_ids[pos] = label;
+        out_sc[score_index(pos, Lp)] = __ddiv_rn((double)cnt, inv_r_den);
+      }
+    }
+    for (int i = kept + tid; i < Lp; i += THREADS) out_ids[i] = KEY_EMPTY;
+    steps = (unsigned long long)block_reduce_sum_ll((long long)steps, S->P.red_a);
+    if (tid == 0) {
+      tot_steps += steps;
+      tot_walks += P.W;
+      tot_bytes += 12ull * steps + 12ull * (unsigned long long)kept + 4ull;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (tot_steps) atomicAdd(&st->walk_steps, tot_steps);
+    if (tot_walks) atomicAdd(&st->walks, tot_walks);
+    if (tot_bytes) atomicAdd(&st->walk_bytes, tot_bytes);
+    if (tot_truncs) atomicAdd(&st->truncs, tot_truncs);
+    if (tot_ties) atomicAdd(&st->ties, tot_ties);
+    if (tot_requeue) atomicAdd(&st->requeues, tot_requeue);
+  }
+}
+
+}  // namespace pprb200

@@ -6,12 +6,14 @@
 // (iter_end clears RunState::active, later launches return immediately).
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <numeric>
 #include <vector>
 
+#include "mc_walk.cuh"
 #include "merge_par.cuh"
 #include "ppr_internal.h"
 
@@ -205,6 +207,9 @@ struct pprb200_session {
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   std::vector<cudaEvent_t> ev_merge;  // pairs (begin,end) per iteration
   uint32_t merge_launches = 0;
+  cudaEvent_t ev_walk[2] = {nullptr, nullptr};
+  unsigned long long* d_walk_ws = nullptr;  // fallback visit-count tables of the MC walk phase
+  size_t walk_ws_bytes = 0;
   uint64_t launch_count = 0;  // kernels enqueued by the last run
   double prep_ms = 0, h2d_ms = 0;
 };
@@ -240,6 +245,8 @@ static void session_free(pprb200_session* s) {
   cudaFree(s->d_ncand); cudaFree(s->d_state); cudaFree(s->d_final_stats); cudaFree(s->d_ws);
   cudaFree(s->d_out_ids); cudaFree(s->d_out_scores); cudaFree(s->d_out_cnt);
   cudaFree(s->d_item_pos); cudaFree(s->d_item_off); cudaFree(s->d_item_len); cudaFree(s->d_pool);
+  cudaFree(s->d_walk_ws);
+  for (int i = 0; i < 2; i++) if (s->ev_walk[i]) cudaEventDestroy(s->ev_walk[i]);
   cudaFree(s->d_prof); cudaFree(s->d_tbl_inuse); cudaFree(s->d_tbl_count); cudaFree(s->d_node_tbl); cudaFree(s->d_node_done);
   if (s->ev_begin) cudaEventDestroy(s->ev_begin);
   if (s->ev_end) cudaEventDestroy(s->ev_end);
@@ -249,7 +256,7 @@ static void session_free(pprb200_session* s) {
 
 static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour_in,
                                uint32_t max_L, uint32_t hub_threshold, int32_t rank, int32_t world, void* stream,
-                               pprb200_session** out) {
+                               pprb200_session** out, bool need_colour = true) {
   if (!out) return fail(PPRB200_ERR_PARAM, "out is NULL");
   *out = nullptr;
   if (max_L == 0) return fail(PPRB200_ERR_PARAM, "L must be positive");
@@ -273,6 +280,7 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
 
   std::vector<uint8_t> colour((size_t)n);
   if (colour_in) std::memcpy(colour.data(), colour_in, (size_t)n);
+  else if (!need_colour) std::fill(colour.begin(), colour.end(), (uint8_t)0);  // MC-only session: one class
   else if ((rc = find_partitions(row_ptr, col, n, colour.data()))) { delete s; return rc; }
   for (int32_t v = 0; v < n; v++) {
     if (colour[v] > 1) { delete s; return fail(PPRB200_ERR_PARAM, "colour[%d] = %d is not 0/1", v, colour[v]); }
@@ -421,6 +429,8 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   cudaMemsetAsync(s->d_ncand, 0, (size_t)std::max(M, 1) * sizeof(int), st);
   cudaEventCreate(&s->ev_begin);
   cudaEventCreate(&s->ev_end);
+  cudaEventCreate(&s->ev_walk[0]);
+  cudaEventCreate(&s->ev_walk[1]);
   if (getenv("PPRB200_PROF")) {
     if ((rc = dev_alloc(&s->d_prof, (size_t)2 * s->sm_count * 3 * 8))) { session_free(s); return rc; }
     cudaMemsetAsync(s->d_prof, 0, (size_t)2 * s->sm_count * 3 * 8 * sizeof(unsigned long long), st);
@@ -671,6 +681,133 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
   return PPRB200_OK;
 }
 
+
+// ---- MCCompletePathV2 (mccompletepathv2.h:182-258, north-star semantics) ---------------------------------------
+template <bool GLOBAL>
+static cudaError_t launch_walk(pprb200_session* s, const WalkParams& P, int grid, size_t smem) {
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(mc_walk_kernel<GLOBAL, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  mc_walk_kernel<GLOBAL, 256><<<grid, 256, smem, s->stream>>>(P);
+  s->launch_count++;
+  return cudaGetLastError();
+}
+
+static uint32_t mc_coin_threshold(double damping) {
+  const double t = std::floor(damping * 4294967296.0);
+  if (t >= 4294967295.0) return 0xFFFFFFFFu;
+  if (t <= 0) return 0u;
+  return (uint32_t)t;
+}
+
+static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t R, double damping, uint64_t seed, uint32_t rounds) {
+  int rc = check_params(K, L, R, damping);
+  if (rc) return rc;
+  if (L > s->max_L) return fail(PPRB200_ERR_PARAM, "L=%u exceeds the session's max_L=%u", L, s->max_L);
+  if ((size_t)roundup4((int)L) * 12 > 200 * 1024) return fail(PPRB200_ERR_PARAM, "L=%u is above this build's limit of 17064", L);
+  if ((rc = ensure_outputs(s, K))) return rc;
+  s->last_mode = MODE_MC;
+  s->last_K = K; s->last_L = L; s->last_iterations = rounds;
+  while (s->ev_merge.size() < 2 * (size_t)std::max<uint32_t>(rounds, 1)) { cudaEvent_t e; cudaEventCreate(&e); s->ev_merge.push_back(e); }
+  s->merge_launches = 0;
+  const int Lp = roundup4((int)L);
+  const unsigned long long W = (unsigned long long)((double)R * damping);  // mccompletepathv2.h:132
+
+  cudaStream_t st = s->stream;
+  cudaEventRecord(s->ev_begin, st);
+  state_reset_kernel<<<1, 1, 0, st>>>(s->d_state);
+  s->launch_count = 1;
+  cudaEventRecord(s->ev_walk[0], st);
+  if (s->M > 0) {
+    WalkParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.g.row_off = s->d_row_off; P.g.col = s->d_col; P.g.label = s->d_label; P.g.dense_of = s->d_dense_of;
+    P.buf[0] = s->d_buf[0]; P.buf[1] = s->d_buf[1];
+    P.st = s->d_state;
+    P.M = s->M; P.src_begin = 0; P.src_end = s->M;
+    P.colour = s->d_colour;
+    P.Lp = Lp; P.L = (int)L; P.R = R; P.W = W; P.thresh = mc_coin_threshold(damping); P.seed = seed;
+    // shared-memory table sized for the expected number of distinct visited nodes (<= hops + 1)
+    const double len = damping >= 1.0 ? (double)MC_MAX_STEPS : std::min<double>((double)MC_MAX_STEPS, 1.0 / (1.0 - damping));
+    const double expect = std::min<double>((double)s->n + 1.0, 1.0 + (double)W * len * 0.8);
+    unsigned int tcap = 1024;
+    while ((double)tcap * 0.75 < expect && tcap < 16384u) tcap <<= 1;
+    if (const char* e = getenv("PPRB200_WALK_TCAP")) {  // test hook: force the fallback path
+      unsigned int want = (unsigned int)std::max(1024, atoi(e));
+      tcap = 1024;
+      while (tcap < want && tcap < 16384u) tcap <<= 1;
+    }
+    P.tcap = tcap; P.limit = tcap * 3 / 4 - 1;
+    P.work_idx = 0; P.queue_in = nullptr; P.queue_in_idx = -1; P.queue_out = s->d_queue[0]; P.queue_out_idx = 0;
+    const size_t smem = ((sizeof(WalkShared) + 15) & ~(size_t)15) + (size_t)tcap * sizeof(WalkSlot);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (smem + 1024)));
+    cudaError_t e = launch_walk<false>(s, P, std::max(1, std::min(s->M, s->sm_count * per_sm)), smem);
+    if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "mc_walk launch failed: %s", cudaGetErrorString(e));
+    // fallback: sources that visited more distinct nodes than the shared table admits
+    const unsigned long long worst = std::min<unsigned long long>((unsigned long long)s->n + 1ull, W * (unsigned long long)MC_MAX_STEPS + 1ull);
+    if (worst > P.limit) {
+      unsigned long long cap = 2048;
+      while (cap < 2 * worst) cap <<= 1;
+      const size_t per = (size_t)cap * sizeof(WalkSlot);
+      const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)s->sm_count, ((size_t)2 << 30) / per));
+      if ((size_t)grid * per > s->walk_ws_bytes) {
+        cudaFree(s->d_walk_ws);
+        s->d_walk_ws = nullptr; s->walk_ws_bytes = 0;
+        if ((rc = dev_alloc(&s->d_walk_ws, (size_t)grid * cap))) return rc;
+        s->walk_ws_bytes = (size_t)grid * per;
+      }
+      WalkParams Q = P;
+      Q.tcap = (unsigned int)cap; Q.limit = 0xffffffffu;
+      Q.work_idx = 1; Q.queue_in = s->d_queue[0]; Q.queue_in_idx = 0; Q.queue_out = nullptr; Q.queue_out_idx = 0;
+      Q.ws = s->d_walk_ws;
+      e = launch_walk<true>(s, Q, grid, (sizeof(WalkShared) + 15) & ~(size_t)15);
+      if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "mc_walk fallback launch failed: %s", cudaGetErrorString(e));
+    }
+    phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 1, 0);
+    s->launch_count++;
+  }
+  cudaEventRecord(s->ev_walk[1], st);
+
+  // combine rounds (mccompletepathv2.h:211-250 as Jacobi sweeps over all nodes)
+  MergeParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.g.row_off = s->d_row_off; P.g.col = s->d_col; P.g.label = s->d_label; P.g.dense_of = s->d_dense_of;
+  P.buf[0] = s->d_buf[0]; P.buf[1] = s->d_buf[1];
+  P.st = s->d_state;
+  P.mode = MODE_MC;
+  P.damping = damping;
+  P.self_grank = 1.0 - damping;
+  P.ncand = s->d_ncand;
+  if (s->M > 0 && rounds > 0) cudaMemsetAsync(s->d_ncand, 0, (size_t)s->M * sizeof(int), st);
+  for (uint32_t r = 0; r < rounds; r++) {
+    cudaEventRecord(s->ev_merge[2 * r], st);
+    if (s->M > 0) {
+      for (int c = 0; c < 2; c++) {
+        MergeParams Q = P;
+        Q.init_mode = 0; Q.do_norm = 0; Q.colour = c;
+        if ((rc = enqueue_par(s, Q, c, (int)L))) return rc;
+        if (s->range_end[c] > s->range_begin[c] && (rc = enqueue_cascade(s, Q, s->range_begin[c], s->range_end[c], (int)L))) return rc;
+        // both colours read the same (old) buffer: counters are cleared between the two cascades, slots flip at the end
+        phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 0, c == 1 ? 1 : 0);
+        s->launch_count++;
+      }
+    } else {
+      phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 0, 1);
+      s->launch_count++;
+    }
+    cudaEventRecord(s->ev_merge[2 * r + 1], st);
+  }
+  s->merge_launches = rounds;
+  if ((rc = enqueue_final(s, (int)L, K, 1.0))) return rc;
+  cudaEventRecord(s->ev_end, st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "enqueue failed: %s", cudaGetErrorString(e));
+  return PPRB200_OK;
+}
+
 static int session_stats_impl(pprb200_session* s, pprb200_stats* out) {
   if (!out) return fail(PPRB200_ERR_PARAM, "stats is NULL");
   std::memset(out, 0, sizeof(*out));
@@ -698,6 +835,7 @@ static int session_stats_impl(pprb200_session* s, pprb200_stats* out) {
   out->walk_steps = h.walk_steps;
   out->walks = h.walks;
   out->overflow_requeues = h.requeues;
+  out->walk_algorithmic_bytes = h.walk_bytes;
   // maxDiff pair as grank.h leaves it: [0] = older, [1] = latest (after the swap of :140)
   out->max_diff[0] = h.m_prev < 0 ? 0.0 : (double)h.m_prev * NORM_INV;
   out->max_diff[1] = h.m_last < 0 ? 0.0 : (double)h.m_last * NORM_INV;
@@ -752,8 +890,9 @@ int pprb200_session_grank(pprb200_session* s, uint32_t K, uint32_t L, uint32_t i
 }
 
 int pprb200_session_mc(pprb200_session* s, uint32_t K, uint32_t L, uint32_t R, double damping, uint64_t seed, uint32_t rounds) {
-  (void)s; (void)K; (void)L; (void)R; (void)damping; (void)seed; (void)rounds;
-  return fail(PPRB200_ERR_STATE, "MC path not built yet");
+  if (!s) return fail(PPRB200_ERR_PARAM, "session is NULL");
+  std::lock_guard<std::mutex> lk(g_api_mutex);
+  return session_mc_impl(s, K, L, R, damping, seed, rounds);
 }
 
 int pprb200_session_fetch(pprb200_session* s, int32_t* out_ids, double* out_scores, uint32_t* out_cnt) {
@@ -773,6 +912,13 @@ int pprb200_session_kernel_time(pprb200_session* s, int which, uint32_t* launche
   std::lock_guard<std::mutex> lk(g_api_mutex);
   if (s->last_mode < 0) return fail(PPRB200_ERR_STATE, "no run has been enqueued on this session");
   CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (which == 1) {
+    float ms = 0;
+    if (s->last_mode != MODE_MC || cudaEventElapsedTime(&ms, s->ev_walk[0], s->ev_walk[1]) != cudaSuccess) ms = 0;
+    if (launches) *launches = s->last_mode == MODE_MC ? 1u : 0u;
+    if (total_ms) *total_ms = ms;
+    return PPRB200_OK;
+  }
   if (which != 0) return fail(PPRB200_ERR_PARAM, "which=%d unknown", which);
   RunState h;
   CUDA_TRY(cudaMemcpy(&h, s->d_state, sizeof(h), cudaMemcpyDeviceToHost));
@@ -838,10 +984,32 @@ int pprb200_grank(const int64_t* row_ptr, const int32_t* col, int32_t n, const u
 int pprb200_mccompletepathv2(const int64_t* row_ptr, const int32_t* col, int32_t n, uint32_t K, uint32_t L, uint32_t R,
                              double damping, uint64_t seed, uint32_t rounds, uint32_t hub_threshold, int32_t* out_ids,
                              double* out_scores, uint32_t* out_cnt, pprb200_stats* stats) {
-  (void)row_ptr; (void)col; (void)n; (void)seed; (void)rounds; (void)hub_threshold; (void)out_ids; (void)out_scores; (void)out_cnt; (void)stats;
-  int rc = check_params(K, L, R, damping);
+  int rc = check_params(K, L, R, damping);  // before touching the graph (mccompletepathv2.h:190-194)
   if (rc) return rc;
-  return fail(PPRB200_ERR_STATE, "MC path not built yet");
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (n == 0) return PPRB200_OK;
+  const double t0 = now_ms();
+  pprb200_session* s = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    rc = session_create_impl(row_ptr, col, n, nullptr, L, hub_threshold, 0, 1, nullptr, &s, /*need_colour=*/false);
+    if (rc) return rc;
+    rc = session_mc_impl(s, K, L, R, damping, seed, rounds);
+    double t_d2h = 0;
+    if (!rc) {
+      cudaStreamSynchronize(s->stream);
+      const double t1 = now_ms();
+      rc = session_fetch_impl(s, out_ids, out_scores, out_cnt);
+      t_d2h = now_ms() - t1;
+    }
+    if (!rc && stats) {
+      rc = session_stats_impl(s, stats);
+      stats->d2h_ms = t_d2h;
+    }
+    session_free(s);
+  }
+  if (!rc && stats) stats->total_ms = now_ms() - t0;
+  return rc;
 }
 
 }  // extern "C"

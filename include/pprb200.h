@@ -60,6 +60,7 @@ typedef struct pprb200_stats {
   uint64_t walk_steps;              /* MC: hops executed (mccompletepathv2.h:149) */
   uint64_t walks;                   /* MC: walks started */
   uint64_t overflow_requeues;       /* node-iterations that had to be retried with a larger hash table */
+  uint64_t walk_algorithmic_bytes;  /* MC walk phase, SURVEY.md 8(d): 12 B per hop + 12*|basket| + 4 per source */
   double max_diff[2];               /* final maxDiff pair (grank.h:90,140) */
   double prep_ms;                   /* host: partition + storage order + CSR encode */
   double h2d_ms;
