@@ -45,8 +45,71 @@ struct RunState {
   unsigned long long node_iters, edge_reads, merged, cands, truncs, ties, abytes, requeues;
   unsigned long long walk_steps, walks, walk_bytes;
   unsigned int ws_next;      // bump allocator for the global-table workspace
-  unsigned int pad;
+  int peer_timeout;          // set when a cross-GPU barrier gave up waiting
 };
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU: one process per GPU; every GPU holds the whole CSR and both basket buffers and owns
+// every world-th node of each class (interleaved over the degree-sorted storage order). A node's new basket is
+// written locally and PUSHED into the same slot of every peer's buffer with plain stores through NVLink peer
+// mappings (cudaIpc) by the warp / CTA that produced it -- the allgather of the reference design is fused into the
+// merge / walk kernels' epilogue and overlaps the rest of the grid's work. Iterations are separated by a mailbox
+// barrier (cross_gpu_barrier) that also carries the max-diff of the convergence test.
+// ------------------------------------------------------------------------------------------------
+constexpr int MAX_WORLD = 8;
+
+struct Mailbox {  // one per (parity, sender rank), written by the sender, polled by the owner
+  unsigned long long seq;
+  long long value;
+};
+
+struct PeerDev {
+  int world, rank;
+  unsigned char* buf[MAX_WORLD][2];  // peer basket buffers (entry [rank] = the local ones)
+  Mailbox* mbox[MAX_WORLD];          // peer mailboxes: mbox[r][parity * MAX_WORLD + sender]
+};
+
+// copy the freshly written slot of position p to every peer; `lane`/`nlanes` = the calling warp or CTA.
+// The caller must have made the local slot visible to all calling threads (__syncwarp / __syncthreads).
+__device__ __forceinline__ void publish_slot(const PeerDev& pd, int which_buf, size_t slot_off, size_t bytes, int lane, int nlanes) {
+  if (pd.world <= 1) return;
+  const int4* src = reinterpret_cast<const int4*>(pd.buf[pd.rank][which_buf] + slot_off);
+  const int n16 = (int)(bytes >> 4);
+  for (int i = lane; i < n16; i += nlanes) {
+    const int4 v = __ldcg(src + i);
+    for (int r = 0; r < pd.world; r++)
+      if (r != pd.rank) __stcg(reinterpret_cast<int4*>(pd.buf[r][which_buf] + slot_off) + i, v);
+  }
+}
+
+// One thread of one CTA: tell every peer that this rank finished step `seq` (with `value`), wait for all of them,
+// return the max of the values. Relies on stream order: the kernels that pushed this step's slots have completed,
+// so their peer stores are performed before the flag store below is issued.
+__device__ inline long long cross_gpu_barrier(const PeerDev& pd, unsigned long long seq, long long value, int* timed_out) {
+  if (pd.world <= 1) return value;
+  const int par = (int)(seq & 1ull);
+  __threadfence_system();
+  for (int r = 0; r < pd.world; r++) {
+    Mailbox* m = pd.mbox[r] + par * MAX_WORLD + pd.rank;
+    *reinterpret_cast<volatile long long*>(&m->value) = value;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(&m->seq) = seq;
+  }
+  __threadfence_system();
+  long long best = value;
+  const long long t0 = clock64();
+  for (int r = 0; r < pd.world; r++) {
+    const Mailbox* m = pd.mbox[pd.rank] + par * MAX_WORLD + r;
+    while (*reinterpret_cast<const volatile unsigned long long*>(&m->seq) != seq) {
+      if (clock64() - t0 > 60000000000ll) { *timed_out = 1; return best; }  // ~30 s: a peer died
+      __nanosleep(200);
+    }
+    __threadfence_system();
+    const long long v = *reinterpret_cast<const volatile long long*>(&m->value);
+    best = v > best ? v : best;
+  }
+  return best;
+}
 
 struct GraphDev {
   const long long* row_off;  // [M+1]

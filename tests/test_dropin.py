@@ -1,0 +1,97 @@
+"""The drop-in boundary: tests/cpp/dropin_check.cc is ONE user program written against the
+reference's public API; it is compiled twice -- against the reference's headers (oracle/_ref/dropin_check_ref) and
+against ours (tests/cpp/dropin_check_b200, linking libppr_b200.so) -- and must behave the same.
+
+CPU part: the parameter "death tests" (same stderr text, exit status 1, before any device work) and the empty graph.
+GPU part: every case's result maps equal the reference build's (committed under tests/golden/dropin/, and the live
+reference binary where it exists): identical key sets, |score difference| <= 1e-9."""
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+OURS = ROOT / "tests" / "cpp" / "dropin_check_b200"
+REF = ROOT / "oracle" / "_ref" / "dropin_check_ref"
+GOLDEN = ROOT / "tests" / "golden" / "dropin"
+TOL = 1e-9
+
+DEATH = {0: "K must be positive", 1: "L must be positive", 2: "K must be <= L", 3: "iterations must be positive",
+         4: "damping must be [0,1]", 5: "damping must be [0,1]", 6: "nThreads must be positive", 7: "K must be positive",
+         8: "K must be positive", 9: "iterations must be positive", 10: "K must be <= L", 11: "damping must be [0,1]"}
+CASES = ["readme_ring", "no_edges", "self_loop", "ring6", "star", "ring100", "random_full", "multi_equals_single", "string_keys",
+         "long_keys"]
+
+
+def run(binary, *args):
+    return subprocess.run([str(binary), *args], capture_output=True, text=True, timeout=600)
+
+
+def parse(text):
+    """-> list of (case name, {key: {key: score}})"""
+    out, cur = [], None
+    for line in text.splitlines():
+        if line.startswith("case "):
+            cur = {}
+            out.append((line.split()[1], cur))
+        elif line.startswith("multi"):
+            cur[line] = {}
+        elif ":" in line:
+            k, rest = line.split(":", 1)
+            cur[k] = {kv.rsplit("=", 1)[0]: float(kv.rsplit("=", 1)[1]) for kv in rest.split()}
+    return out
+
+
+def assert_same(a, b, what):
+    assert [n for n, _ in a] == [n for n, _ in b], what
+    for (name, ra), (_, rb) in zip(a, b):
+        assert ra.keys() == rb.keys(), f"{what}/{name}: node sets differ"
+        for node in ra:
+            assert ra[node].keys() == rb[node].keys(), f"{what}/{name}: basket membership of {node} differs"
+            for k in ra[node]:
+                assert abs(ra[node][k] - rb[node][k]) <= TOL, f"{what}/{name}: {node}->{k}: {ra[node][k]} vs {rb[node][k]}"
+
+
+@pytest.mark.parametrize("which", sorted(DEATH))
+def test_bad_parameters_print_the_reference_message_and_exit_1(which):
+    r = run(OURS, "death", str(which))
+    assert r.returncode == 1 and r.stderr.strip() == DEATH[which] and "survived" not in r.stdout
+    if REF.exists():
+        q = run(REF, "death", str(which))
+        assert (q.returncode, q.stderr) == (r.returncode, r.stderr)
+
+
+def test_empty_graph_gives_empty_maps_without_a_gpu():
+    r = run(OURS, "empty")
+    assert r.returncode == 0 and r.stdout == (GOLDEN / "empty.txt").read_text()
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    """without a usable sm_100 device a compute call must fail loudly (message + exit 1), never compute on the host"""
+    import ctypes
+    from approximated_personalized_pagerank_b200 import _lib
+    if _lib.load().pprb200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    r = run(OURS, "self_loop")
+    assert r.returncode == 1 and "no CUDA device" in r.stderr and "case" not in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+def test_same_results_as_the_reference_build(case):
+    r = run(OURS, case)
+    assert r.returncode == 0, r.stderr
+    ours = parse(r.stdout)
+    assert_same(ours, parse((GOLDEN / f"{case}.txt").read_text()), f"golden {case}")
+    if REF.exists():
+        q = run(REF, case)
+        assert q.returncode == 0
+        assert_same(ours, parse(q.stdout), f"live reference {case}")
+
+
+@pytest.mark.gpu
+def test_mc_structural_cases_hold_for_both_builds():
+    r = run(OURS, "mc_structural")
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+    if REF.exists():
+        assert run(REF, "mc_structural").returncode == 0
