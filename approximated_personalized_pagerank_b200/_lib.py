@@ -97,11 +97,15 @@ def load():
     lib.pprb200_session_kernel_time.argtypes = [c_void_p, c_int, C.POINTER(c_uint32), C.POINTER(c_double)]
     lib.pprb200_session_launches.argtypes = [c_void_p, C.POINTER(c_uint64)]
     lib.pprb200_session_launches.restype = c_int
+    lib.pprb200_session_ipc_export.argtypes = [c_void_p, c_void_p]
+    lib.pprb200_session_ipc_attach.argtypes = [c_void_p, c_void_p]
+    lib.pprb200_shard_owner.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_uint32, c_int32, c_void_p]
     lib.pprb200_gen_rmat.argtypes = [c_uint32, c_uint32, c_uint64, c_double, c_double, c_double, c_void_p, c_void_p]
     lib.pprb200_gen_ba.argtypes = [c_int32, c_uint32, c_uint64, c_void_p, c_void_p, C.POINTER(c_int64)]
     for name in ("pprb200_find_partitions", "pprb200_grank", "pprb200_mccompletepathv2", "pprb200_session_create",
                  "pprb200_session_grank", "pprb200_session_mc", "pprb200_session_fetch", "pprb200_session_stats",
-                 "pprb200_session_kernel_time", "pprb200_gen_rmat", "pprb200_gen_ba"):
+                 "pprb200_session_kernel_time", "pprb200_gen_rmat", "pprb200_gen_ba", "pprb200_session_ipc_export",
+                 "pprb200_session_ipc_attach", "pprb200_shard_owner"):
         getattr(lib, name).restype = c_int
     _lib = lib
     return lib

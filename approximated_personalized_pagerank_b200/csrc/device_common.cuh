@@ -46,6 +46,7 @@ struct RunState {
   unsigned long long walk_steps, walks, walk_bytes;
   unsigned int ws_next;      // bump allocator for the global-table workspace
   int peer_timeout;          // set when a cross-GPU barrier gave up waiting
+  unsigned long long barrier_seq;  // executed cross-GPU barriers (kept across runs)
 };
 
 // ------------------------------------------------------------------------------------------------

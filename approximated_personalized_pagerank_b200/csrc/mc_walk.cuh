@@ -41,6 +41,7 @@ struct WalkParams {
   unsigned int* queue_out;    // nullable (fallback launch never overflows)
   int queue_out_idx;
   unsigned long long* ws;     // fallback: gridDim.x tables of tcap 64-bit slots
+  PeerDev peers;              // multi-GPU: source index i of this rank maps to position src_begin + i*world + rank
 };
 
 struct WalkSlot {
@@ -88,7 +89,11 @@ __global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
 
   unsigned int total;
   if (P.queue_in_idx >= 0) total = st->qcount[P.queue_in_idx];
-  else total = (unsigned int)(P.src_end - P.src_begin);
+  else {
+    const int len = P.src_end - P.src_begin, w = P.peers.world > 1 ? P.peers.world : 1, r = P.peers.world > 1 ? P.peers.rank : 0;
+    total = len > r ? (unsigned int)((len - r + w - 1) / w) : 0u;
+  }
+  const int stride = P.peers.world > 1 ? P.peers.world : 1, offset = P.peers.world > 1 ? P.peers.rank : 0;
   const int write_slot = st->slot[0];
   unsigned long long tot_steps = 0, tot_walks = 0, tot_bytes = 0, tot_truncs = 0, tot_ties = 0, tot_requeue = 0;
 
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
     __syncthreads();
     const unsigned int item = S->item;
     if (item >= total) break;
-    const int p = (P.queue_in_idx >= 0) ? (int)P.queue_in[item] : P.src_begin + (int)item;
+    const int p = (P.queue_in_idx >= 0) ? (int)P.queue_in[item] : P.src_begin + (int)item * stride + offset;
     const int self_label = P.g.label[p];
     const uint32_t src_dense = (uint32_t)P.g.dense_of[self_label];
     const uint32_t self_word = (uint32_t)p | ((uint32_t)P.colour[src_dense] << COL_COLOUR_SHIFT);
@@ -210,6 +215,8 @@ __global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
       }
     }
     for (int i = kept + tid; i < Lp; i += THREADS) out_ids[i] = KEY_EMPTY;
+    __syncthreads();
+    publish_slot(P.peers, write_slot, (size_t)p * slot_bytes(Lp), slot_bytes(Lp), tid, THREADS);
     steps = (unsigned long long)block_reduce_sum_ll((long long)steps, S->P.red_a);
     if (tid == 0) {
       tot_steps += steps;

@@ -39,6 +39,8 @@ struct MergeParams {
   int limit;                       // max distinct candidates this launch may hold (<= CAP - Lp - 1)
   int* ncand;                      // [M] distinct-candidate count of the node's latest update (class prediction)
   int do_norm;                     // GRank: 1; MC: 0
+  PeerDev peers;                   // multi-GPU peers that receive every basket this launch writes
+  const int* work_list;            // multi-GPU: this rank's positions of the range (range = indices into the list)
   int init_mode;                   // GRank init (grank.h:64-83): every successor s contributes {s: +factor}; writes the current slot
 };
 
@@ -282,6 +284,7 @@ __device__ bool merge_node_seq(const MergeParams& P, const WarpTable<IdxT>& T, u
     if (dsum > warp_maxdiff) warp_maxdiff = dsum;
   }
   __syncwarp();
+  publish_slot(P.peers, write_slot, (size_t)p * slot_bytes(Lp), slot_bytes(Lp), lane, 32);
   // reset the table through the occupied-slot list
   for (int i = lane; i < n; i += 32) T.keys[T.list[i]] = KEY_EMPTY;
   if (lane == 0) {
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(WARPS * 32) merge_seq_kernel(MergeParams P, un
       __syncwarp();
       table_clean = true;
     }
-    const int p = (P.queue_in_idx >= 0) ? (int)P.queue_in[idx] : P.range_begin + (int)idx;
+    const int p = (P.queue_in_idx >= 0) ? (int)P.queue_in[idx] : (P.work_list ? P.work_list[P.range_begin + (int)idx] : P.range_begin + (int)idx);
     bool ok = false;
     // class prediction: a node whose previous candidate count already exceeds this table goes straight on
     const bool skip = P.queue_out != nullptr && P.ncand[p] > P.limit;

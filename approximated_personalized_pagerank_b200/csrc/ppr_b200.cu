@@ -35,7 +35,9 @@ static double now_ms() {
 // ------------------------------------------------------------------------------------------------
 __global__ void state_reset_kernel(RunState* st) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const unsigned long long seq = st->barrier_seq;  // survives across runs: all ranks count executed barriers in lockstep
     memset(st, 0, sizeof(RunState));
+    st->barrier_seq = seq;
     st->active = 1;
     st->m_prev = -1;
     st->m_last = -1;
@@ -43,8 +45,10 @@ __global__ void state_reset_kernel(RunState* st) {
 }
 
 // end of an init / combine phase: clear cascade counters (and optionally the work statistics)
-__global__ void phase_end_kernel(RunState* st, int clear_stats, int flip_both) {
+__global__ void phase_end_kernel(RunState* st, int clear_stats, int flip_both, PeerDev peers, int barrier) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    // multi-GPU: every rank's pushes of this phase have landed before anybody reads them (or overwrites their source)
+    if (barrier && peers.world > 1) cross_gpu_barrier(peers, ++st->barrier_seq, 0, &st->peer_timeout);
     for (int i = 0; i < 8; i++) st->work[i] = 0;
     for (int i = 0; i < 4; i++) st->qcount[i] = 0;
     if (clear_stats) {
@@ -55,11 +59,14 @@ __global__ void phase_end_kernel(RunState* st, int clear_stats, int flip_both) {
 }
 
 // end of GRank iteration `it` (0-based) on `colour`: grank.h:129-140 + the loop test of :92
-__global__ void iter_end_kernel(RunState* st, int colour, double tolerance) {
+__global__ void iter_end_kernel(RunState* st, int colour, double tolerance, PeerDev peers) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     for (int i = 0; i < 8; i++) st->work[i] = 0;
     for (int i = 0; i < 4; i++) st->qcount[i] = 0;
     if (!st->active) return;
+    // multi-GPU: barrier + allreduce(max) of the iteration's max-diff in one mailbox round; every rank takes the
+    // same decision below, so converged runs skip the remaining barriers consistently
+    if (peers.world > 1) st->cur_max = cross_gpu_barrier(peers, ++st->barrier_seq, st->cur_max, &st->peer_timeout);
     st->slot[colour] ^= 1;
     st->iter++;
     st->m_prev = st->m_last;
@@ -159,6 +166,11 @@ struct pprb200_session {
   int64_t E = 0;
   uint32_t max_L = 0, hub_threshold = 0;
   int rank = 0, world = 1;
+  PeerDev peers;                    // device view of the peer mappings (world 1: zeroed)
+  int* d_seq_list = nullptr;        // world > 1: own positions of the exact-order class (range_begin/end index it)
+  Mailbox* d_mbox = nullptr;        // [2][MAX_WORLD] barrier mailboxes of this rank, written by the peers
+  void* ipc_opened[MAX_WORLD][3];   // peer mappings to close
+  bool attached = false;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   // storage ranges [colour]: exact-order class (out-degree <= hub_threshold), stored first
@@ -239,6 +251,11 @@ static int dev_alloc(T** p, size_t count) {
 
 static void session_free(pprb200_session* s) {
   if (!s) return;
+  for (int r = 0; r < MAX_WORLD; r++)
+    for (int i = 0; i < 3; i++)
+      if (s->ipc_opened[r][i]) cudaIpcCloseMemHandle(s->ipc_opened[r][i]);
+  cudaFree(s->d_mbox);
+  cudaFree(s->d_seq_list);
   cudaFree(s->d_row_off); cudaFree(s->d_col); cudaFree(s->d_label); cudaFree(s->d_pos_of); cudaFree(s->d_dense_of); cudaFree(s->d_colour);
   cudaFree(s->d_buf[0]); cudaFree(s->d_buf[1]);
   for (int i = 0; i < 3; i++) cudaFree(s->d_queue[i]);
@@ -254,13 +271,59 @@ static void session_free(pprb200_session* s) {
   delete s;
 }
 
+static int default_mid_deg() {
+  if (const char* e = getenv("PPRB200_MID_DEG")) return std::max(1, atoi(e));
+  return 64;
+}
+
+// storage positions of the non-sink nodes: colour-major, then class (0 exact-order, 1 mid, 2 big), then out-degree
+// descending (ties by dense id)
+// owner_of_pos (world > 1): longest-processing-time-first over each (colour, class) list, work = out-degree, so that
+// every iteration's merged entries are balanced up to the single largest node.
+static void storage_order(const int64_t* row_ptr, int32_t n, const uint8_t* colour, uint32_t hub_threshold, int mid_deg,
+                          std::vector<int32_t>& order, int cls_begin[2][3], int cls_end[2][3], int world = 1,
+                          std::vector<int32_t>* owner_of_pos = nullptr) {
+  order.clear();
+  order.reserve((size_t)n);
+  for (int c = 0; c < 2; c++)
+    for (int cls = 0; cls < 3; cls++) {
+      const size_t b = order.size();
+      cls_begin[c][cls] = (int)b;
+      for (int32_t v = 0; v < n; v++) {
+        const int64_t d = row_ptr[v + 1] - row_ptr[v];
+        if (colour[v] != c || d == 0) continue;
+        const int k = (uint64_t)d <= (uint64_t)hub_threshold ? 0 : (d <= mid_deg ? 1 : 2);
+        if (k == cls) order.push_back(v);
+      }
+      std::stable_sort(order.begin() + (long)b, order.end(), [&](int32_t x, int32_t y) {
+        return (row_ptr[x + 1] - row_ptr[x]) > (row_ptr[y + 1] - row_ptr[y]);
+      });
+      cls_end[c][cls] = (int)order.size();
+    }
+  if (owner_of_pos) {
+    owner_of_pos->assign(order.size(), 0);
+    if (world > 1)
+      for (int c = 0; c < 2; c++) {
+        std::vector<long long> load((size_t)world, 0);  // carried across the classes of one colour: they run back to back
+        for (int cls = 2; cls >= 0; cls--)
+          for (int p = cls_begin[c][cls]; p < cls_end[c][cls]; p++) {
+            int best = 0;
+            for (int r = 1; r < world; r++)
+              if (load[r] < load[best]) best = r;
+            (*owner_of_pos)[(size_t)p] = best;
+            load[best] += row_ptr[order[(size_t)p] + 1] - row_ptr[order[(size_t)p]];
+          }
+      }
+  }
+}
+
 static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour_in,
                                uint32_t max_L, uint32_t hub_threshold, int32_t rank, int32_t world, void* stream,
                                pprb200_session** out, bool need_colour = true) {
   if (!out) return fail(PPRB200_ERR_PARAM, "out is NULL");
   *out = nullptr;
   if (max_L == 0) return fail(PPRB200_ERR_PARAM, "L must be positive");
-  if (world != 1 || rank != 0) return fail(PPRB200_ERR_PARAM, "multi-rank sessions are not available in this build (world=%d)", world);
+  if (world < 1 || world > MAX_WORLD || rank < 0 || rank >= world) return fail(PPRB200_ERR_PARAM, "rank %d / world %d: need 0 <= rank < world <= %d", rank, world, MAX_WORLD);
   int rc = validate_csr(row_ptr, col, n);
   if (rc) return rc;
   rc = device_ok();
@@ -268,6 +331,8 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
 
   const double t0 = now_ms();
   pprb200_session* s = new pprb200_session();
+  std::memset(&s->peers, 0, sizeof(s->peers));
+  std::memset(s->ipc_opened, 0, sizeof(s->ipc_opened));
   s->n = n;
   s->max_L = max_L;
   s->hub_threshold = hub_threshold == 0 ? PPRB200_DEFAULT_HUB_THRESHOLD : hub_threshold;
@@ -290,27 +355,22 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   // storage order: colour-major; inside a colour the exact-order class first, then the order-free class
   // (mid, big); every class by out-degree descending (ties by dense id) -- big nodes first for load balance
   if (const char* e = getenv("PPRB200_CHUNK")) s->chunk = std::max(32, atoi(e));
-  if (const char* e = getenv("PPRB200_MID_DEG")) s->mid_deg = std::max(1, atoi(e));
+  s->mid_deg = default_mid_deg();
   std::vector<int32_t> order;
-  order.reserve((size_t)n);
   int cls_begin[2][3], cls_end[2][3];
+  std::vector<int32_t> owner_of_pos;
+  storage_order(row_ptr, n, colour.data(), s->hub_threshold, s->mid_deg, order, cls_begin, cls_end, world, &owner_of_pos);
+  std::vector<int> seq_list;  // world > 1: this rank's positions of the exact-order class, colour-major
   for (int c = 0; c < 2; c++) {
-    for (int cls = 0; cls < 3; cls++) {
-      const size_t b = order.size();
-      cls_begin[c][cls] = (int)b;
-      for (int32_t v = 0; v < n; v++) {
-        const int64_t d = row_ptr[v + 1] - row_ptr[v];
-        if (colour[v] != c || d == 0) continue;
-        const int k = (uint64_t)d <= (uint64_t)s->hub_threshold ? 0 : (d <= s->mid_deg ? 1 : 2);
-        if (k == cls) order.push_back(v);
-      }
-      std::stable_sort(order.begin() + (long)b, order.end(), [&](int32_t x, int32_t y) {
-        return (row_ptr[x + 1] - row_ptr[x]) > (row_ptr[y + 1] - row_ptr[y]);
-      });
-      cls_end[c][cls] = (int)order.size();
+    if (world == 1) {
+      s->range_begin[c] = cls_begin[c][0];
+      s->range_end[c] = cls_end[c][0];
+    } else {
+      s->range_begin[c] = (int)seq_list.size();
+      for (int p = cls_begin[c][0]; p < cls_end[c][0]; p++)
+        if (owner_of_pos[(size_t)p] == rank) seq_list.push_back(p);
+      s->range_end[c] = (int)seq_list.size();
     }
-    s->range_begin[c] = cls_begin[c][0];
-    s->range_end[c] = cls_end[c][0];
   }
   // rank labels: in-degree descending, ties by dense id (the keys stored in the baskets)
   std::vector<int32_t> dense_of((size_t)n), rank_of((size_t)n);
@@ -340,6 +400,7 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
     for (int cls = 1; cls < 3; cls++) {
       s->item_begin[c][cls - 1] = (int)item_pos.size();
       for (int p = cls_begin[c][cls]; p < cls_end[c][cls]; p++) {
+        if (owner_of_pos[(size_t)p] != rank) continue;  // multi-GPU: somebody else's node
         const long long d = row_off[(size_t)p + 1] - row_off[p];
         if (d > s->max_deg_par) s->max_deg_par = (int32_t)std::min<long long>(d, INT32_MAX);
         for (long long o = 0; o < d; o += s->chunk) {
@@ -352,7 +413,7 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
     }
   s->n_items = (int)item_pos.size();
   for (int c = 0; c < 2; c++)
-    for (int p = s->range_begin[c]; p < s->range_end[c]; p++)
+    for (int p = cls_begin[c][0]; p < cls_end[c][0]; p++)
       s->max_deg_seq = std::max<int32_t>(s->max_deg_seq, (int32_t)std::min<long long>(row_off[(size_t)p + 1] - row_off[p], INT32_MAX));
   std::vector<uint32_t> enc((size_t)std::max<int64_t>(E, 1));
   for (int32_t p = 0; p < M; p++) {
@@ -393,6 +454,10 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   if (n) UP(s->d_dense_of, dense_of.data(), (size_t)n * sizeof(int));
   if (n) UP(s->d_pos_of, pos_of.data(), (size_t)n * sizeof(int));
   if (n) UP(s->d_colour, colour.data(), (size_t)n);
+  if (world > 1) {
+    if ((rc = dev_alloc(&s->d_seq_list, seq_list.size()))) { session_free(s); return rc; }
+    if (!seq_list.empty()) UP(s->d_seq_list, seq_list.data(), seq_list.size() * sizeof(int));
+  }
   if (s->n_items > 0) {
     const int Lpm = roundup4((int)max_L);
     const unsigned long long worst = std::min<unsigned long long>(2ull * ((unsigned long long)s->max_deg_par * Lpm + 2ull),
@@ -427,6 +492,9 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   cudaError_t e = cudaStreamSynchronize(st);  // host vectors go out of scope
   if (e != cudaSuccess) { session_free(s); return fail(PPRB200_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e)); }
   cudaMemsetAsync(s->d_ncand, 0, (size_t)std::max(M, 1) * sizeof(int), st);
+  if ((rc = dev_alloc(&s->d_mbox, (size_t)2 * MAX_WORLD))) { session_free(s); return rc; }
+  cudaMemsetAsync(s->d_mbox, 0, sizeof(Mailbox) * 2 * MAX_WORLD, st);
+  cudaMemsetAsync(s->d_state, 0, sizeof(RunState), st);
   cudaEventCreate(&s->ev_begin);
   cudaEventCreate(&s->ev_end);
   cudaEventCreate(&s->ev_walk[0]);
@@ -630,6 +698,7 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
   if (L > s->max_L) return fail(PPRB200_ERR_PARAM, "L=%u exceeds the session's max_L=%u", L, s->max_L);
   if ((size_t)roundup4((int)L) * 12 > 200 * 1024) return fail(PPRB200_ERR_PARAM, "L=%u is above this build's limit of 17064", L);
   if ((rc = ensure_outputs(s, K))) return rc;
+  if (s->world > 1 && !s->attached) return fail(PPRB200_ERR_STATE, "world=%d session: call pprb200_session_ipc_attach before running", s->world);
   s->last_mode = MODE_GRANK;
   s->last_K = K; s->last_L = L; s->last_iterations = iterations;
   while (s->ev_merge.size() < 2 * (size_t)iterations) { cudaEvent_t e; cudaEventCreate(&e); s->ev_merge.push_back(e); }
@@ -639,6 +708,10 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
   cudaEventRecord(s->ev_begin, st);
   state_reset_kernel<<<1, 1, 0, st>>>(s->d_state);
   s->launch_count = 1;
+  if (s->world > 1) {  // nobody overwrites a buffer a slower peer is still reading for its previous run's top-K
+    phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 0, 0, s->peers, 1);
+    s->launch_count++;
+  }
   MergeParams P;
   std::memset(&P, 0, sizeof(P));
   P.g.row_off = s->d_row_off; P.g.col = s->d_col; P.g.label = s->d_label; P.g.dense_of = s->d_dense_of;
@@ -648,6 +721,8 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
   P.damping = damping;
   P.self_grank = 1.0 - damping;
   P.ncand = s->d_ncand;
+  P.peers = s->peers;
+  P.work_list = s->d_seq_list;
   if (s->M > 0) {
     // init (grank.h:64-83)
     cudaMemsetAsync(s->d_ncand, 0, (size_t)s->M * sizeof(int), st);
@@ -656,7 +731,7 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
       Q.init_mode = 1; Q.do_norm = 0; Q.colour = c;
       if ((rc = enqueue_par(s, Q, c, (int)L))) return rc;
       if (s->range_end[c] > s->range_begin[c] && (rc = enqueue_cascade(s, Q, s->range_begin[c], s->range_end[c], (int)L))) return rc;
-      phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 1, 0);
+      phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 1, 0, s->peers, c == 1);
       s->launch_count++;
     }
   }
@@ -670,7 +745,7 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
       if (s->range_end[c] > s->range_begin[c] && (rc = enqueue_cascade(s, Q, s->range_begin[c], s->range_end[c], (int)L))) return rc;
     }
     cudaEventRecord(s->ev_merge[2 * it + 1], st);
-    iter_end_kernel<<<1, 1, 0, st>>>(s->d_state, c, tolerance);
+    iter_end_kernel<<<1, 1, 0, st>>>(s->d_state, c, tolerance, s->peers);
     s->launch_count++;
   }
   s->merge_launches = iterations;
@@ -709,6 +784,7 @@ static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t 
   if (L > s->max_L) return fail(PPRB200_ERR_PARAM, "L=%u exceeds the session's max_L=%u", L, s->max_L);
   if ((size_t)roundup4((int)L) * 12 > 200 * 1024) return fail(PPRB200_ERR_PARAM, "L=%u is above this build's limit of 17064", L);
   if ((rc = ensure_outputs(s, K))) return rc;
+  if (s->world > 1 && !s->attached) return fail(PPRB200_ERR_STATE, "world=%d session: call pprb200_session_ipc_attach before running", s->world);
   s->last_mode = MODE_MC;
   s->last_K = K; s->last_L = L; s->last_iterations = rounds;
   while (s->ev_merge.size() < 2 * (size_t)std::max<uint32_t>(rounds, 1)) { cudaEvent_t e; cudaEventCreate(&e); s->ev_merge.push_back(e); }
@@ -720,6 +796,10 @@ static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t 
   cudaEventRecord(s->ev_begin, st);
   state_reset_kernel<<<1, 1, 0, st>>>(s->d_state);
   s->launch_count = 1;
+  if (s->world > 1) {
+    phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 0, 0, s->peers, 1);
+    s->launch_count++;
+  }
   cudaEventRecord(s->ev_walk[0], st);
   if (s->M > 0) {
     WalkParams P;
@@ -729,6 +809,7 @@ static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t 
     P.st = s->d_state;
     P.M = s->M; P.src_begin = 0; P.src_end = s->M;
     P.colour = s->d_colour;
+    P.peers = s->peers;
     P.Lp = Lp; P.L = (int)L; P.R = R; P.W = W; P.thresh = mc_coin_threshold(damping); P.seed = seed;
     // shared-memory table sized for the expected number of distinct visited nodes (<= hops + 1)
     const double len = damping >= 1.0 ? (double)MC_MAX_STEPS : std::min<double>((double)MC_MAX_STEPS, 1.0 / (1.0 - damping));
@@ -766,7 +847,7 @@ static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t 
       e = launch_walk<true>(s, Q, grid, (sizeof(WalkShared) + 15) & ~(size_t)15);
       if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "mc_walk fallback launch failed: %s", cudaGetErrorString(e));
     }
-    phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 1, 0);
+    phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 1, 0, s->peers, 1);
     s->launch_count++;
   }
   cudaEventRecord(s->ev_walk[1], st);
@@ -781,6 +862,8 @@ static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t 
   P.damping = damping;
   P.self_grank = 1.0 - damping;
   P.ncand = s->d_ncand;
+  P.peers = s->peers;
+  P.work_list = s->d_seq_list;
   if (s->M > 0 && rounds > 0) cudaMemsetAsync(s->d_ncand, 0, (size_t)s->M * sizeof(int), st);
   for (uint32_t r = 0; r < rounds; r++) {
     cudaEventRecord(s->ev_merge[2 * r], st);
@@ -791,11 +874,11 @@ static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t 
         if ((rc = enqueue_par(s, Q, c, (int)L))) return rc;
         if (s->range_end[c] > s->range_begin[c] && (rc = enqueue_cascade(s, Q, s->range_begin[c], s->range_end[c], (int)L))) return rc;
         // both colours read the same (old) buffer: counters are cleared between the two cascades, slots flip at the end
-        phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 0, c == 1 ? 1 : 0);
+        phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 0, c == 1 ? 1 : 0, s->peers, c == 1);
         s->launch_count++;
       }
     } else {
-      phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 0, 1);
+      phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 0, 1, s->peers, 0);
       s->launch_count++;
     }
     cudaEventRecord(s->ev_merge[2 * r + 1], st);
@@ -941,6 +1024,68 @@ int pprb200_debug_prof(pprb200_session* s, unsigned long long* out, int* n_ctas)
   cudaMemcpy(out, s->d_prof, cnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   cudaMemset(s->d_prof, 0, cnt * sizeof(unsigned long long));
   if (n_ctas) *n_ctas = s->sm_count * 3;
+  return PPRB200_OK;
+}
+
+// ---- multi-GPU wiring: CUDA IPC handles of the two basket buffers and the mailbox ----------------------------------
+int pprb200_session_ipc_export(pprb200_session* s, void* out) {
+  if (!s || !out) return fail(PPRB200_ERR_PARAM, "NULL argument");
+  std::lock_guard<std::mutex> lk(g_api_mutex);
+  cudaIpcMemHandle_t h[3];
+  CUDA_TRY(cudaIpcGetMemHandle(&h[0], s->d_buf[0]));
+  CUDA_TRY(cudaIpcGetMemHandle(&h[1], s->d_buf[1]));
+  CUDA_TRY(cudaIpcGetMemHandle(&h[2], s->d_mbox));
+  static_assert(sizeof(h) == PPRB200_IPC_BYTES, "PPRB200_IPC_BYTES");
+  std::memcpy(out, h, sizeof(h));
+  return PPRB200_OK;
+}
+
+int pprb200_session_ipc_attach(pprb200_session* s, const void* all_handles) {
+  if (!s || !all_handles) return fail(PPRB200_ERR_PARAM, "NULL argument");
+  std::lock_guard<std::mutex> lk(g_api_mutex);
+  if (s->attached) return fail(PPRB200_ERR_STATE, "peers already attached");
+  PeerDev pd;
+  std::memset(&pd, 0, sizeof(pd));
+  pd.world = s->world;
+  pd.rank = s->rank;
+  for (int r = 0; r < s->world; r++) {
+    if (r == s->rank) {
+      pd.buf[r][0] = s->d_buf[0]; pd.buf[r][1] = s->d_buf[1]; pd.mbox[r] = s->d_mbox;
+      continue;
+    }
+    cudaIpcMemHandle_t h[3];
+    std::memcpy(h, (const unsigned char*)all_handles + (size_t)r * PPRB200_IPC_BYTES, sizeof(h));
+    for (int i = 0; i < 3; i++) {
+      void* ptr = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, h[i], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d, object %d) failed: %s", r, i, cudaGetErrorString(e));
+      s->ipc_opened[r][i] = ptr;
+    }
+    pd.buf[r][0] = (unsigned char*)s->ipc_opened[r][0];
+    pd.buf[r][1] = (unsigned char*)s->ipc_opened[r][1];
+    pd.mbox[r] = (Mailbox*)s->ipc_opened[r][2];
+  }
+  s->peers = pd;
+  s->attached = true;
+  return PPRB200_OK;
+}
+
+// which rank of `world` updates node v (-1: sinks, nobody), exactly as the sessions shard the work
+int pprb200_shard_owner(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour_in, uint32_t hub_threshold,
+                        int32_t world, int32_t* owner) {
+  if (world < 1 || world > MAX_WORLD) return fail(PPRB200_ERR_PARAM, "world must be 1..%d", MAX_WORLD);
+  int rc = validate_csr(row_ptr, col, n);
+  if (rc) return rc;
+  if (!owner) return fail(PPRB200_ERR_PARAM, "owner is NULL");
+  std::vector<uint8_t> colour((size_t)n, 0);
+  if (colour_in) std::memcpy(colour.data(), colour_in, (size_t)n);
+  std::vector<int32_t> order;
+  int cls_begin[2][3], cls_end[2][3];
+  std::vector<int32_t> owner_of_pos;
+  storage_order(row_ptr, n, colour.data(), hub_threshold == 0 ? PPRB200_DEFAULT_HUB_THRESHOLD : hub_threshold, default_mid_deg(), order,
+                cls_begin, cls_end, world, &owner_of_pos);
+  for (int32_t v = 0; v < n; v++) owner[v] = -1;
+  for (size_t p = 0; p < order.size(); p++) owner[order[p]] = owner_of_pos[p];
   return PPRB200_OK;
 }
 

@@ -124,6 +124,21 @@ int pprb200_session_stats(pprb200_session* s, pprb200_stats* stats);
  * stream: which = 0 merge (GRank iterations / MC combine), 1 MC walks. Returns launches and total ms. */
 int pprb200_session_kernel_time(pprb200_session* s, int which, uint32_t* launches, double* total_ms);
 
+/* ---- multi-GPU: one process (rank) per GPU, sources sharded, baskets pushed to the peers over NVLink ---------
+ * Every rank creates a session with its (rank, world) on its own device, exports PPRB200_IPC_BYTES of CUDA IPC
+ * handles, the host plumbing all-gathers them (torch.distributed / MPI / a file -- not this library's business),
+ * and every rank attaches the world*PPRB200_IPC_BYTES blob (rank-major). All ranks must then enqueue the same
+ * runs in the same order; the kernels exchange baskets and the convergence flag themselves. The caller keeps
+ * every session alive until all ranks have synchronised their last run (peers write into this rank's memory). */
+#define PPRB200_IPC_BYTES 192
+#define PPRB200_MAX_WORLD 8
+int pprb200_session_ipc_export(pprb200_session* s, void* out /* PPRB200_IPC_BYTES */);
+int pprb200_session_ipc_attach(pprb200_session* s, const void* all_handles /* world * PPRB200_IPC_BYTES */);
+/* owner[v] = rank that updates node v in a world-rank session (-1 for sinks: nobody). Host only. colour may be
+ * NULL (MC sessions: one class). */
+int pprb200_shard_owner(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour, uint32_t hub_threshold,
+                        int32_t world, int32_t* owner);
+
 /* Kernels the last run enqueued on the session stream (bench.py's gpu_launches). */
 int pprb200_session_launches(pprb200_session* s, uint64_t* launches);
 
