@@ -54,6 +54,8 @@ WORKLOADS = {
     "ba8m": dict(kind="grank", gen="ba", scale=8388608, K=50, L=100, iterations=30, damping=0.85, tolerance=-1.0,
                  desc="GRank on Barabasi-Albert 8M nodes m=4 symmetrised (BASELINE configs[4])"),
 }
+COUNTERS = ("nonsink_node_iterations", "edge_reads", "merged_entries", "candidates", "truncations", "boundary_ties",
+            "overflow_requeues", "walk_steps", "walks")
 REFERENCE_SAMPLE_ITERATIONS = 4  # iterations per reference step (bounded sample of the 30-iteration job)
 
 
@@ -249,10 +251,13 @@ def main():
     steps = max(1, args.steps)
 
     g = make_graph(w)
-    colour = ppr.find_partitions_csr(g) if w["kind"] == "grank" else None
+    colour = ppr.find_partitions_csr(g) if w["kind"] == "grank" else np.zeros(g.n, dtype=np.uint8)
     stream = torch.cuda.current_stream()
     sess = ppr.Session(g, w["L"], colour=colour, hub_threshold=args.hub_threshold, rank=rank, world=world,
                        stream=stream.cuda_stream)
+    if world > 1:
+        from approximated_personalized_pagerank_b200 import multigpu
+        multigpu.connect(sess, dist)  # CUDA IPC handles of the basket buffers travel over the process group
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def one_step():
@@ -274,7 +279,7 @@ def main():
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    merge_ms, merge_launches, abytes, units, launches = 0.0, 0, 0, 0, 0
+    merge_ms, merge_launches, abytes, units, launches, walk_ms, walk_bytes = 0.0, 0, 0, 0, 0, 0.0, 0
     barrier()
     t_wall0 = time.perf_counter()
     for i in range(steps):
@@ -287,16 +292,27 @@ def main():
         st = sess.stats()
         l, ms = sess.kernel_time(0)
         merge_ms += ms; merge_launches += l; abytes += st["algorithmic_bytes"]; launches += sess.launches()
+        if w["kind"] == "mc":
+            walk_ms += sess.kernel_time(1)[1]; walk_bytes += st["walk_algorithmic_bytes"]
         units += st["node_iterations"] if w["kind"] == "grank" else st["walk_steps"]
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall0)
     clocks = sampler.stop() if rank == 0 else None
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, merge_ms, walk_ms], dtype=torch.float64, device="cuda")
+    stats = sess.stats()
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
-    stats = sess.stats()
+        # per-rank shards of the job -> whole-job totals (node_iterations is already global: colour sizes x iterations)
+        tot = torch.tensor([abytes, walk_bytes, launches, units if w["kind"] == "mc" else 0] +
+                           [stats[k] for k in COUNTERS], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tot)
+        abytes, walk_bytes, launches = int(tot[0]), int(tot[1]), int(tot[2])
+        if w["kind"] == "mc":
+            units = int(tot[3])
+        for i, k in enumerate(COUNTERS):
+            stats[k] = int(tot[4 + i])
+    dev_ms, merge_ms, walk_ms = (float(x) for x in t.tolist())
 
     # ---- e2e: host buffers through the one-shot C-ABI, pinned staging, H2D/D2H inside the timed region ----
     e2e = None
@@ -333,10 +349,60 @@ def main():
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(n * K * 12 + n * 4), "ms_per_step": 1e3 * sec / e_steps,
                "host_prep_ms": st.prep_ms, "kernel_ms": st.kernel_ms, "d2h_ms": st.d2h_ms}
 
+    if world > 1 and not args.no_e2e:
+        # N GPUs end to end through the public multi-GPU API: every rank preprocesses + uploads the CSR from host memory,
+        # the ranks exchange IPC handles, run, and rank 0 reads the whole result back
+        from approximated_personalized_pagerank_b200 import multigpu
+        n, K = g.n, w["K"]
+        ids = torch.empty((n, K), dtype=torch.int32).pin_memory().numpy()
+        sc = torch.empty((n, K), dtype=torch.float64).pin_memory().numpy()
+        cnt = torch.empty(n, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+
+        def e2e_multi():
+            s2 = ppr.Session(g, w["L"], colour=None if w["kind"] == "grank" else np.zeros(n, dtype=np.uint8),
+                             hub_threshold=args.hub_threshold, rank=rank, world=world, stream=stream.cuda_stream)
+            multigpu.connect(s2, dist)
+            if w["kind"] == "grank":
+                s2.grank(K, w["L"], w["iterations"], w["damping"], w["tolerance"])
+            else:
+                s2.mc(K, w["L"], w["iterations"], w["damping"])
+            if rank == 0:
+                s2.fetch(ids, sc, cnt)
+            st2 = s2.stats()
+            torch.cuda.synchronize()
+            dist.barrier()
+            s2.close()
+            return st2["node_iterations"] if w["kind"] == "grank" else st2["walk_steps"]
+        e2e_multi()
+        barrier()
+        t0 = time.perf_counter()
+        e_steps = max(1, min(steps, 3))
+        u = sum(e2e_multi() for _ in range(e_steps))
+        barrier()
+        sec = time.perf_counter() - t0
+        tu = torch.tensor([u if w["kind"] == "mc" else 0], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tu)
+        u = int(tu[0]) if w["kind"] == "mc" else u
+        e2e = {"value": u / sec, "unit": "node-iterations/s" if w["kind"] == "grank" else "walk-steps/s",
+               "h2d_bytes_per_step": int(world * (g.row_ptr.nbytes + g.col.nbytes + g.n * 5)), "d2h_bytes_per_step": int(n * K * 12 + n * 4),
+               "ms_per_step": 1e3 * sec / e_steps}
+
+    def finish():
+        if world > 1:
+            dist.barrier()
+            sess.close()
+            dist.destroy_process_group()
+
     if rank != 0:
+        finish()
         return
     peak, peak_src = measured_peak()
-    achieved = (abytes / 1e9) / (merge_ms / 1e3) if merge_ms > 0 else None
+    peak *= world  # aggregate HBM bandwidth of the GPUs that share the job
+    if w["kind"] == "mc":  # dominant kernel of the MC path by BASELINE's metric: the walk kernel (12 B per hop)
+        rl_bytes, rl_ms, rl_kernel = walk_bytes, walk_ms, "mc_walk_kernel (12 B/hop + basket writes); combine rounds reported under roofline.combine"
+    else:
+        rl_bytes, rl_ms, rl_kernel = abytes, merge_ms, "merge kernels (merge_par_kernel + merge_seq_kernel cascade), all launches of a step"
+    achieved = (rl_bytes / 1e9) / (rl_ms / 1e3) if rl_ms > 0 else None
     metric, unit = ("grank_node_iterations_per_s", "node-iterations/s") if w["kind"] == "grank" else ("mc_walk_steps_per_s", "walk-steps/s")
     line = {
         "metric": metric, "value": units / (dev_ms / 1e3), "unit": unit, "n_gpus": world, "steps": steps, "warmup": warm,
@@ -348,18 +414,19 @@ def main():
                    "sharding": "single GPU" if world == 1 else f"sources sharded over {world} GPUs"},
         "wall_ms_per_step_incl_flush_and_stat_reads": wall_ms / steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                     "traffic": None, "peak_source": peak_src, "kernel": "merge cascade (merge_seq_kernel<...>), all launches of a step",
-                     "algorithmic_bytes_per_step": abytes // steps, "merge_ms_per_step": merge_ms / steps,
-                     "merge_launch_groups_per_step": merge_launches // steps},
+                     "traffic": None, "peak_source": peak_src, "kernel": rl_kernel,
+                     "algorithmic_bytes_per_step": rl_bytes // steps, "kernel_ms_per_step": rl_ms / steps,
+                     "share_of_step": rl_ms / dev_ms if dev_ms > 0 else None,
+                     "combine": ({"achieved": (abytes / 1e9) / (merge_ms / 1e3) if merge_ms > 0 else None, "unit": "GB/s",
+                                  "ms_per_step": merge_ms / steps, "algorithmic_bytes_per_step": abytes // steps}
+                                 if w["kind"] == "mc" else None)},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "counters": {k: stats[k] for k in ("nonsink_node_iterations", "edge_reads", "merged_entries", "candidates", "truncations",
-                                          "boundary_ties", "overflow_requeues", "walk_steps", "walks")},
+        "counters": {k: stats[k] for k in COUNTERS},
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(w, g)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":
