@@ -26,6 +26,7 @@ struct WalkParams {
   unsigned char* buf[2];
   RunState* st;
   int M;                      // sources = non-sink storage positions 0..M-1 (this rank: [src_begin, src_end))
+  int n_ids;                  // number of nodes
   int src_begin, src_end;
   const unsigned char* colour;  // [n] colour by dense id (a node's own column word carries it)
   int Lp, L;

@@ -95,8 +95,15 @@ __device__ unsigned long long block_radix_select(int n, int k, KeyFn key, PredFn
   const int tid = threadIdx.x, T = blockDim.x;
   unsigned long long lo = ~0ull, hi = 0ull;
   long long cnt = 0;
-  for (int i = tid; i < n; i += T)
-    if (pred(i)) { const unsigned long long b = key(i); lo = b < lo ? b : lo; hi = b > hi ? b : hi; cnt++; }
+  for (int i0 = tid; i0 < n; i0 += 4 * T) {  // four independent loads in flight per thread (the keys may live in L2)
+    unsigned long long b[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int i = i0 + u * T; ok[u] = i < n && pred(i); b[u] = ok[u] ? key(i) : 0ull; }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (ok[u]) { lo = b[u] < lo ? b[u] : lo; hi = b[u] > hi ? b[u] : hi; cnt++; }
+  }
   lo = block_reduce_min_ull(lo, S->red_a);
   hi = block_reduce_max_ull(hi, S->red_a);
   *tie = false;
@@ -113,11 +120,15 @@ __device__ unsigned long long block_radix_select(int n, int k, KeyFn key, PredFn
   for (;;) {
     for (int i = tid; i < 256; i += T) S->hist[i] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += T)
-      if (pred(i)) {
-        const unsigned long long b = key(i);
-        if ((b & known) == prefix) atomicAdd(&S->hist[(unsigned)(b >> shift) & 0xffu], 1u);
-      }
+    for (int i0 = tid; i0 < n; i0 += 4 * T) {
+      unsigned long long b[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const int i = i0 + u * T; ok[u] = i < n && pred(i); b[u] = ok[u] ? key(i) : 0ull; }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (ok[u] && (b[u] & known) == prefix) atomicAdd(&S->hist[(unsigned)(b[u] >> shift) & 0xffu], 1u);
+    }
     __syncthreads();
     if (tid < 32) {
       const int lane = tid;
@@ -162,20 +173,43 @@ __device__ __forceinline__ double par_score(unsigned long long acc, bool init_mo
   return a;
 }
 
-__device__ __forceinline__ void gtable_add(GSlot* slots, unsigned int* glist, unsigned int* gcount, unsigned int mask,
-                                           int identity, int k, unsigned long long x) {
+// accumulate x on key k of a global table; returns true when this call inserted the key (slot in *slot): the caller
+// appends the slot to the table's first-touch list (glist_append: one counter atomic per warp, not per key)
+__device__ __forceinline__ bool gtable_upsert(GSlot* slots, unsigned int mask, int identity, int k, unsigned long long x,
+                                              unsigned int* slot) {
   unsigned int h = (identity ? (unsigned int)k : hash_key(k)) & mask;
+  bool inserted = false;
   for (;;) {
     const int cur = *reinterpret_cast<volatile int*>(&slots[h].key);
     if (cur == k) break;
     if (cur == KEY_EMPTY) {
       const int old = atomicCAS(&slots[h].key, KEY_EMPTY, k);
-      if (old == KEY_EMPTY) { const unsigned int pos = atomicAdd(gcount, 1u); glist[pos] = h; break; }
+      if (old == KEY_EMPTY) { inserted = true; break; }
       if (old == k) break;
     }
     h = (h + 1) & mask;
   }
   if (x) atomicAdd(&slots[h].acc, x);
+  *slot = h;
+  return inserted;
+}
+
+// all 32 lanes call
+__device__ __forceinline__ void glist_append(bool inserted, unsigned int slot, unsigned int* glist, unsigned int* gcount) {
+  const unsigned m = __ballot_sync(FULL, inserted);
+  if (!m) return;
+  const int lane = lane_id(), leader = __ffs(m) - 1;
+  unsigned int base = 0;
+  if (lane == leader) base = atomicAdd(gcount, (unsigned int)__popc(m));
+  base = __shfl_sync(FULL, base, leader);
+  if (inserted) glist[base + __popc(m & ((1u << lane) - 1u))] = slot;
+}
+
+// any thread on its own (divergent callers)
+__device__ __forceinline__ void gtable_add(GSlot* slots, unsigned int* glist, unsigned int* gcount, unsigned int mask,
+                                           int identity, int k, unsigned long long x) {
+  unsigned int h;
+  if (gtable_upsert(slots, mask, identity, k, x, &h)) glist[atomicAdd(gcount, 1u)] = h;
 }
 
 __device__ __forceinline__ int gtable_find(const GSlot* slots, unsigned int mask, int identity, int k) {
@@ -195,27 +229,48 @@ __device__ __forceinline__ void fixed_add_shared(uint2* word, unsigned long long
   if (hi) atomicAdd(&word->y, hi);
 }
 
-template <int H, int TCAP>
+constexpr int PAR_CHUNK_MAX = 1024;  // successors per work item of the big class (column words are staged in shared memory)
+constexpr int PAR_MID_MAX = 128;     // largest out-degree the mid class may be configured for
+
+template <int H, int TCAP, int CMAX, int COLCAP>
 constexpr size_t par_smem_bytes() {
-  return (size_t)H * 8 + (size_t)TCAP * 14 + (size_t)H / 8 + sizeof(ParShared);
+  return (size_t)H * 8 + (size_t)TCAP * 14 + (size_t)H / 8 + (size_t)CMAX * 12 + (size_t)COLCAP * 4 + sizeof(ParShared);
+}
+constexpr size_t par_queue_bytes(int threads) { return (size_t)(threads / 32) * 64 * 12; }
+
+// unconditional fetch of lane g's four entries (three independent 16-byte loads; unused entries hold id -1 and
+// whatever score bytes were there -- never looked at)
+__device__ __forceinline__ void load_frag_all(const unsigned char* slot, int Lp, int g, BasketFrag* f) {
+  const int4* ids = reinterpret_cast<const int4*>(slot);
+  const double2* sc = reinterpret_cast<const double2*>(slot + (size_t)Lp * 4);
+  f->id = __ldg(ids + g);
+  f->sa = __ldg(sc + g);
+  f->sb = __ldg(sc + (Lp >> 2) + g);
 }
 
-// H dense labels, TCAP tail slots, THREADS threads. TLIMIT distinct tail keys are admitted (concurrent inserts
-// may overshoot by < THREADS).
-template <int H, int TCAP, int THREADS>
+// H dense labels, TCAP tail slots (TLIMIT distinct tail keys admitted; concurrent inserts may overshoot by < THREADS),
+// CMAX compact candidates, COLCAP staged column words (>= successors per work item), THREADS threads.
+template <int H, int TCAP, int CMAX, int COLCAP, int THREADS>
 __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
   constexpr int TLIMIT = TCAP * 13 / 16 - THREADS;
   constexpr int NW = THREADS / 32;
+  static_assert(H + TCAP <= 65536, "candidate references are 16 bit");
   extern __shared__ __align__(16) unsigned char smem[];
   const MergeParams& M = P.M;
   RunState* st = M.st;
   if (!st->active) return;
-  uint2* s_dense = reinterpret_cast<uint2*>(smem);
-  uint2* t_acc = reinterpret_cast<uint2*>(smem + (size_t)H * 8);
-  int* t_keys = reinterpret_cast<int*>(smem + (size_t)H * 8 + (size_t)TCAP * 8);
-  unsigned short* t_list = reinterpret_cast<unsigned short*>(smem + (size_t)H * 8 + (size_t)TCAP * 12);
-  unsigned int* s_zbits = reinterpret_cast<unsigned int*>(smem + (size_t)H * 8 + (size_t)TCAP * 14);  // touched with a 0 word
-  ParShared* S = reinterpret_cast<ParShared*>(smem + (size_t)H * 8 + (size_t)TCAP * 14 + (size_t)H / 8);
+  unsigned char* sp = smem;
+  uint2* s_dense = reinterpret_cast<uint2*>(sp); sp += (size_t)H * 8;
+  uint2* t_acc = reinterpret_cast<uint2*>(sp); sp += (size_t)TCAP * 8;
+  unsigned long long* c_bits = reinterpret_cast<unsigned long long*>(sp); sp += (size_t)CMAX * 8;  // compact candidates: score bits
+  int* t_keys = reinterpret_cast<int*>(sp); sp += (size_t)TCAP * 4;
+  int* c_id = reinterpret_cast<int*>(sp); sp += (size_t)CMAX * 4;                                   //                     labels
+  uint32_t* s_col = reinterpret_cast<uint32_t*>(sp); sp += (size_t)COLCAP * 4;
+  unsigned int* s_zbits = reinterpret_cast<unsigned int*>(sp); sp += (size_t)H / 8;  // dense labels touched with a 0 word
+  unsigned short* t_list = reinterpret_cast<unsigned short*>(sp); sp += (size_t)TCAP * 2;
+  ParShared* S = reinterpret_cast<ParShared*>(sp); sp += (sizeof(ParShared) + 7) & ~(size_t)7;
+  unsigned long long* q_val = reinterpret_cast<unsigned long long*>(sp); sp += (size_t)NW * 64 * 8;  // per-warp slow-entry queues
+  int* q_key = reinterpret_cast<int*>(sp);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int Lp = M.Lp, groups = Lp >> 2, L = M.L;
   const bool init_mode = M.init_mode != 0;
@@ -253,6 +308,7 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
     if (x) fixed_add_shared(&t_acc[h], x);
     return true;
   };
+  auto dense_touched = [&](int i, const uint2& a) -> bool { return ((a.x | a.y) != 0u) || ((s_zbits[i >> 5] >> (i & 31)) & 1u); };
 
   unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long t_last = clock64();
@@ -277,11 +333,14 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
     const double self0 = (M.mode == MODE_GRANK) ? M.self_grank : 1.0;
     const int write_slot = init_mode ? st->slot[M.colour] : (st->slot[M.colour] ^ 1);
 
+    // stage the chunk's column words (coalesced) so that the basket prefetch below never waits on them
+    for (int j = tid; j < clen; j += THREADS) s_col[j] = M.g.col[cb + j];
+
     // lazily bound global table of this node (acquired by the first CTA that needs it)
     GSlot* gslots = nullptr;
     unsigned int* glist = nullptr;
     unsigned int* gcount = nullptr;
-    double* cvals = nullptr;
+    unsigned long long* gbits = nullptr;
     int* cids = nullptr;
     auto bind_table = [&]() {
       if (tid == 0 && S->table < 0) {
@@ -308,7 +367,7 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
       unsigned char* base = P.pool + (size_t)S->table * P.tbl_bytes;
       gslots = reinterpret_cast<GSlot*>(base);
       glist = reinterpret_cast<unsigned int*>(base + (size_t)P.capmax * sizeof(GSlot));
-      cvals = reinterpret_cast<double*>(base + (size_t)P.capmax * (sizeof(GSlot) + 4));
+      gbits = reinterpret_cast<unsigned long long*>(base + (size_t)P.capmax * (sizeof(GSlot) + 4));
       cids = reinterpret_cast<int*>(base + (size_t)P.capmax * (sizeof(GSlot) + 4 + 4));
       gcount = &P.tbl_count[S->table];
     };
@@ -349,7 +408,7 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
       if (init_mode) {
         // grank.h:79-80: every occurrence of a successor adds `factor`; here: multiplicity += 1
         for (int j = tid; j < clen; j += THREADS) {
-          const uint32_t c = M.g.col[cb + j];
+          const uint32_t c = s_col[j];
           const int k = (c & COL_SINK) ? (int)(c & ~COL_SINK) : M.g.label[c & COL_POS_MASK];
           if ((unsigned)k < (unsigned)H) fixed_add_shared(&s_dense[k], 1ull);
           else slow_contribute(k, 1ull, spill_ok);
@@ -357,64 +416,87 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
         }
         return;
       }
-      BasketFrag cur;
-      cur.id = make_int4(-1, -1, -1, -1);
-      cur.sa = cur.sb = make_double2(0.0, 0.0);
-      int j = w;
-      uint32_t c = (j < clen) ? M.g.col[cb + j] : 0u;
-      auto prefetch = [&](uint32_t cc, BasketFrag* fr) {
+      // warp w merges successors w, w+NW, ... with the next two baskets already in flight
+      auto slot_of = [&](uint32_t cc) -> const unsigned char* {
+        return M.buf[read_slot[(cc >> COL_COLOUR_SHIFT) & 1u]] + (size_t)(cc & COL_POS_MASK) * slot_bytes(Lp);
+      };
+      auto fetch = [&](int j, BasketFrag* fr) {
         fr->id = make_int4(-1, -1, -1, -1);
         fr->sa = fr->sb = make_double2(0.0, 0.0);
-        if (!(cc & COL_SINK) && lane < groups) {
-          const unsigned char* slot = M.buf[read_slot[(cc >> COL_COLOUR_SHIFT) & 1u]] + (size_t)(cc & COL_POS_MASK) * slot_bytes(Lp);
-          load_frag(slot, Lp, lane, fr);
+        if (j < clen) {
+          const uint32_t cc = s_col[j];
+          if (!(cc & COL_SINK) && lane < groups) load_frag_all(slot_of(cc), Lp, lane, fr);
         }
       };
-      if (j < clen) prefetch(c, &cur);
-      for (; j < clen; j += NW) {  // warp w merges successors w, w+NW, ... with the next basket already in flight
-        const uint32_t cn = (j + NW < clen) ? M.g.col[cb + j + NW] : 0u;
-        BasketFrag nxt;
-        nxt.id = make_int4(-1, -1, -1, -1);
-        nxt.sa = nxt.sb = make_double2(0.0, 0.0);
-        if (j + NW < clen) prefetch(cn, &nxt);
-        if (c & COL_SINK) {
-          if (lane == 0) {
-            const int k = (int)(c & ~COL_SINK);
-            const double x = (M.mode == MODE_GRANK) ? M.self_grank : 1.0;
-            const unsigned long long xf = (unsigned long long)__double2ll_rn(x * fscale);
-            if ((unsigned)k < (unsigned)H && xf) fixed_add_shared(&s_dense[k], xf);
-            else slow_contribute(k, xf, spill_ok);
-            merged++;
+      // Entries that miss the dense range (tail labels, zero products) are rare but slow (hash probe, CAS); taken
+      // inline they would stall the whole warp behind two or three lanes. They are parked in a per-warp queue and
+      // drained 32 at a time with every lane busy.
+      int qn = 0;
+      int* qk = q_key + w * 64;
+      unsigned long long* qv = q_val + w * 64;
+      auto drain = [&](int cnt) {  // the last `cnt` (<= 32) queued entries, one per lane
+        __syncwarp();
+        bool ins = false;
+        unsigned int slot = 0;
+        if (lane < cnt) {
+          const int k = qk[qn - cnt + lane];
+          const unsigned long long x = qv[qn - cnt + lane];
+          if ((unsigned)k < (unsigned)H) atomicOr(&s_zbits[k >> 5], 1u << (k & 31));  // dense label, zero product: touched
+          else if (!tail_add(k, x)) {
+            if (spill_ok) ins = gtable_upsert(gslots, S->gmask, S->gidentity, k, x, &slot);
+            else S->spilled = 1;
           }
+        }
+        if (spill_ok) glist_append(ins, slot, glist, gcount);
+        qn -= cnt;
+        __syncwarp();
+      };
+      auto contribute = [&](int k, unsigned long long xf) {  // called by all 32 lanes; k < 0: nothing
+        const bool fast = (unsigned)k < (unsigned)H && xf != 0ull;
+        if (fast) fixed_add_shared(&s_dense[k], xf);
+        const bool slow = !fast && k >= 0;
+        const unsigned m = __ballot_sync(FULL, slow);
+        if (m) {
+          if (slow) { const int pos = qn + __popc(m & ((1u << lane) - 1u)); qk[pos] = k; qv[pos] = xf; }
+          qn += __popc(m);
+          if (qn >= 32) drain(32);
+        }
+      };
+      BasketFrag f0, f1;
+      fetch(w, &f0);
+      fetch(w + NW, &f1);
+      for (int j = w; j < clen; j += NW) {
+        BasketFrag f2;
+        fetch(j + 2 * NW, &f2);
+        const uint32_t c = s_col[j];
+        if (c & COL_SINK) {
+          const double x = (M.mode == MODE_GRANK) ? M.self_grank : 1.0;
+          contribute(lane == 0 ? (int)(c & ~COL_SINK) : -1, (unsigned long long)__double2ll_rn(x * fscale));
+          merged += (lane == 0);
         } else {
-          const unsigned char* slot = M.buf[read_slot[(c >> COL_COLOUR_SHIFT) & 1u]] + (size_t)(c & COL_POS_MASK) * slot_bytes(Lp);
-          for (int g = lane; g < groups; g += 32) {
+          for (int g0 = 0; g0 < groups; g0 += 32) {
             BasketFrag fr;
-            if (g == lane) fr = cur; else load_frag(slot, Lp, g, &fr);
+            if (g0 == 0) fr = f0;
+            else {
+              fr.id = make_int4(-1, -1, -1, -1);
+              fr.sa = fr.sb = make_double2(0.0, 0.0);
+              if (g0 + lane < groups) load_frag_all(slot_of(c), Lp, g0 + lane, &fr);
+            }
             const int ids[4] = {fr.id.x, fr.id.y, fr.id.z, fr.id.w};
             const double xs[4] = {fr.sa.x, fr.sa.y, fr.sb.x, fr.sb.y};
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-              const int k = ids[e];
-              const unsigned long long xf = (unsigned long long)__double2ll_rn(xs[e] * fscale);
-              if ((unsigned)k < (unsigned)H && xf) fixed_add_shared(&s_dense[k], xf);   // hot path
-              else if (k >= 0) slow_contribute(k, xf, spill_ok);
-              merged += (k >= 0);
+              contribute(ids[e], (unsigned long long)__double2ll_rn(xs[e] * fscale));
+              merged += (ids[e] >= 0);
             }
           }
         }
-        cur = nxt;
-        c = cn;
+        f0 = f1;
+        f1 = f2;
       }
+      if (qn > 0) drain(qn);
     };
-    // a node expected to outgrow the tail table binds its global table up front
-    if (S->table < 0 && M.ncand[p] > TLIMIT + H / 2) bind_table();
-    PROF_MARK(1);
-    accumulate(S->table >= 0);
-    __syncthreads();
-    PROF_MARK(2);
-    if (S->spilled) {
-      // mispredicted: drop the partial sums, bind a table and run the chunk again with spilling enabled
+    auto reset_shared = [&]() {  // drop the partial sums of this item
       __syncthreads();
       for (int i = tid; i < H; i += THREADS) s_dense[i] = make_uint2(0u, 0u);
       for (int i = tid; i < H / 32; i += THREADS) s_zbits[i] = 0u;
@@ -426,6 +508,67 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
       }
       __syncthreads();
       if (tid == 0) { S->tcount = 0; S->spilled = 0; s_requeue++; }
+    };
+    // a node expected to outgrow the shared-memory structures binds its global table up front
+    if (S->table < 0 && M.ncand[p] > (TLIMIT + H / 2 < CMAX ? TLIMIT + H / 2 : CMAX)) bind_table();
+    PROF_MARK(1);
+    accumulate(S->table >= 0);
+    __syncthreads();
+    PROF_MARK(2);
+
+    // single-chunk node that stayed in shared memory: compact the candidates (score bits, label)
+    int n = 0;
+    if (S->table < 0 && !S->spilled) {
+      if (tid == 0) S->ncand = 0;
+      __syncthreads();
+      const double base_self = init_mode ? M.self_grank : 0.0;
+      for (int i0 = 0; i0 < H; i0 += THREADS) {
+        const int i = i0 + tid;
+        const uint2 a = s_dense[i];
+        const bool ok = dense_touched(i, a);
+        const unsigned m = __ballot_sync(FULL, ok);
+        if (m) {
+          int basep = 0;
+          if (lane == (int)(__ffs(m) - 1)) basep = atomicAdd(&S->ncand, __popc(m));
+          basep = __shfl_sync(FULL, basep, __ffs(m) - 1);
+          if (ok) {
+            const int pos = basep + __popc(m & ((1u << lane) - 1u));
+            if (pos < CMAX) {
+              const double v = par_score(((unsigned long long)a.y << 32) | a.x, init_mode, inv, mult, (init_mode && i == self_id) ? base_self : 0.0);
+              c_bits[pos] = (unsigned long long)__double_as_longlong(v);
+              c_id[pos] = i;
+            }
+          }
+        }
+      }
+      const int nt0 = S->tcount;
+      for (int i0 = 0; i0 < nt0; i0 += THREADS) {
+        const int i = i0 + tid;
+        const bool ok = i < nt0;
+        const unsigned m = __ballot_sync(FULL, ok);
+        int basep = 0;
+        if (lane == (int)(__ffs(m) - 1)) basep = atomicAdd(&S->ncand, __popc(m));
+        basep = __shfl_sync(FULL, basep, __ffs(m) - 1);
+        if (ok) {
+          const int pos = basep + __popc(m & ((1u << lane) - 1u));
+          if (pos < CMAX) {
+            const int sl = t_list[i];
+            const int id = t_keys[sl];
+            const double v = par_score(((unsigned long long)t_acc[sl].y << 32) | t_acc[sl].x, init_mode, inv, mult,
+                                       (init_mode && id == self_id) ? base_self : 0.0);
+            c_bits[pos] = (unsigned long long)__double_as_longlong(v);
+            c_id[pos] = id;
+          }
+        }
+      }
+      __syncthreads();
+      n = S->ncand;
+      if (n > CMAX && tid == 0) S->spilled = 1;  // more candidates than the compact arrays hold: take the global path
+      __syncthreads();
+    }
+    if (S->spilled) {
+      // mispredicted: drop the partial sums, bind a table and run the chunk again with spilling enabled
+      reset_shared();
       bind_table();
       put_self();
       __syncthreads();
@@ -436,22 +579,29 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
 
     const int nt = S->tcount;  // occupied tail slots
     const bool use_global = S->table >= 0;
-    int n = 0;
     int kept = 0, old_cnt = 0;
     bool finalize = !use_global;  // single chunk, nothing spilled: finish from shared memory
     if (use_global) {
       // flush the shared accumulators into the node's global table (and leave them clean)
       for (int i = tid; i < H; i += THREADS) {
         const uint2 a = s_dense[i];
-        const bool z = (s_zbits[i >> 5] >> (i & 31)) & 1u;
-        if ((a.x | a.y) || z) {
-          gtable_add(gslots, glist, gcount, S->gmask, S->gidentity, i, ((unsigned long long)a.y << 32) | a.x);
+        bool ins = false;
+        unsigned int slot = 0;
+        if (dense_touched(i, a)) {
+          ins = gtable_upsert(gslots, S->gmask, S->gidentity, i, ((unsigned long long)a.y << 32) | a.x, &slot);
           s_dense[i] = make_uint2(0u, 0u);
         }
+        glist_append(ins, slot, glist, gcount);
       }
-      for (int i = tid; i < nt; i += THREADS) {
-        const int s = t_list[i];
-        gtable_add(gslots, glist, gcount, S->gmask, S->gidentity, t_keys[s], ((unsigned long long)t_acc[s].y << 32) | t_acc[s].x);
+      for (int i0 = 0; i0 < nt; i0 += THREADS) {
+        const int i = i0 + tid;
+        bool ins = false;
+        unsigned int slot = 0;
+        if (i < nt) {
+          const int s = t_list[i];
+          ins = gtable_upsert(gslots, S->gmask, S->gidentity, t_keys[s], ((unsigned long long)t_acc[s].y << 32) | t_acc[s].x, &slot);
+        }
+        glist_append(ins, slot, glist, gcount);
       }
       __threadfence();
       __syncthreads();
@@ -468,58 +618,39 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
 
     if (finalize) {
       const double base_self = init_mode ? M.self_grank : 0.0;
-      // candidates: a virtual index space. shared: [0,H) dense labels (pred: touched), [H, H+nt) tail list;
-      // global: compact arrays gathered once from the table.
-      int nv;
+      // candidates: compact arrays (score bits, label) -- in shared memory, or gathered once from the global table
+      const unsigned long long* kb = c_bits;
+      const int* ki = c_id;
       if (use_global) {
         n = (int)*reinterpret_cast<volatile unsigned int*>(gcount);
-        nv = n;
         for (int i = tid; i < n; i += THREADS) {
           const GSlot g = gslots[glist[i]];
           cids[i] = g.key;
-          cvals[i] = par_score(g.acc, init_mode, inv, mult, (init_mode && g.key == self_id) ? base_self : 0.0);
+          gbits[i] = (unsigned long long)__double_as_longlong(
+              par_score(g.acc, init_mode, inv, mult, (init_mode && g.key == self_id) ? base_self : 0.0));
         }
         __syncthreads();
-      } else {
-        nv = H + nt;
-        int c = 0;
-        for (int i = tid; i < H; i += THREADS) {
-          const uint2 a = s_dense[i];
-          c += ((a.x | a.y) != 0u) || ((s_zbits[i >> 5] >> (i & 31)) & 1u);
-        }
-        n = (int)block_reduce_sum_ll(c, S->red_a) + nt;
+        kb = gbits;
+        ki = cids;
       }
-      auto cand_ok = [&](int i) -> bool {
-        if (use_global || i >= H) return true;
-        const uint2 a = s_dense[i];
-        return ((a.x | a.y) != 0u) || ((s_zbits[i >> 5] >> (i & 31)) & 1u);
-      };
-      auto cand_id = [&](int i) -> int { return use_global ? cids[i] : (i < H ? i : t_keys[t_list[i - H]]); };
-      auto cand_val = [&](int i) -> double {
-        if (use_global) return cvals[i];
-        unsigned long long a;
-        int id;
-        if (i < H) { a = ((unsigned long long)s_dense[i].y << 32) | s_dense[i].x; id = i; }
-        else { const int s = t_list[i - H]; a = ((unsigned long long)t_acc[s].y << 32) | t_acc[s].x; id = t_keys[s]; }
-        return par_score(a, init_mode, inv, mult, (init_mode && id == self_id) ? base_self : 0.0);
-      };
       Threshold th;
       th.bits = 0ull;
       th.id_max = 0x7fffffff;
       kept = n;
+      auto all = [](int) { return true; };
       if (n > L) {
         kept = L;
         bool tie;
         int krem;
-        auto keyfn = [&](int i) { return (unsigned long long)__double_as_longlong(cand_val(i)); };
-        th.bits = block_radix_select(nv, L, keyfn, cand_ok, S, &tie, &krem);
+        auto keyfn = [&](int i) { return kb[i]; };
+        th.bits = block_radix_select(n, L, keyfn, all, S, &tie, &krem);
         if (tie) {
           const unsigned long long tb = th.bits;
-          auto idkey = [&](int i) { return (unsigned long long)(0x7fffffff - dense_of[cand_id(i)]); };
-          auto tied = [&](int i) { return cand_ok(i) && (unsigned long long)__double_as_longlong(cand_val(i)) == tb; };
+          auto idkey = [&](int i) { return (unsigned long long)(0x7fffffff - dense_of[ki[i]]); };
+          auto tied = [&](int i) { return kb[i] == tb; };
           bool tie2;
           int krem2;
-          const unsigned long long tid_key = block_radix_select(nv, krem, idkey, tied, S, &tie2, &krem2);
+          const unsigned long long tid_key = block_radix_select(n, krem, idkey, tied, S, &tie2, &krem2);
           th.id_max = 0x7fffffff - (int)tid_key;
           s_ties += (tid == 0);
         }
@@ -536,12 +667,12 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
       if (tid == 0) S->out_pos = 0;
       __syncthreads();
       long long dsum = 0;
-      for (int i = tid; i < nv; i += THREADS) {
-        if (!cand_ok(i)) continue;
-        const int id = cand_id(i);
-        const double v = cand_val(i);
-        if (selected((unsigned long long)__double_as_longlong(v), id)) {
+      for (int i = tid; i < n; i += THREADS) {
+        const unsigned long long bits = kb[i];
+        const int id = ki[i];
+        if (selected(bits, id)) {
           const int pos = atomicAdd(&S->out_pos, 1);
+          const double v = __longlong_as_double((long long)bits);
           out_ids[pos] = id;
           out_sc[score_index(pos, Lp)] = v;  // hub path: no post-scale (already multiplied by f)
           dsum += fix_norm(v);
@@ -567,7 +698,7 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
                 if (s >= 0) { found = true; nv_ = par_score(gslots[s].acc, false, inv, mult, 0.0); }
               } else if ((unsigned)ids[e] < (unsigned)H) {
                 const uint2 a = s_dense[ids[e]];
-                found = ((a.x | a.y) != 0u) || ((s_zbits[ids[e] >> 5] >> (ids[e] & 31)) & 1u);
+                found = dense_touched(ids[e], a);
                 nv_ = par_score(((unsigned long long)a.y << 32) | a.x, false, inv, mult, 0.0);
               } else {
                 for (unsigned int h = hash_key(ids[e]) & (TCAP - 1);; h = (h + 1) & (TCAP - 1)) {
@@ -605,7 +736,11 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
           atomicExch(&P.tbl_inuse[S->table], 0u);
         }
       } else {
-        for (int i = tid; i < H; i += THREADS) s_dense[i] = make_uint2(0u, 0u);
+        // clear the touched dense words through the compact list
+        for (int i = tid; i < n; i += THREADS) {
+          const int id = c_id[i];
+          if ((unsigned)id < (unsigned)H) s_dense[id] = make_uint2(0u, 0u);
+        }
         for (int i = tid; i < H / 32; i += THREADS) s_zbits[i] = 0u;
       }
       if (tid == 0) {

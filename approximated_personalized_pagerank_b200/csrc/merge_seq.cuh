@@ -41,6 +41,7 @@ struct MergeParams {
   int do_norm;                     // GRank: 1; MC: 0
   PeerDev peers;                   // multi-GPU peers that receive every basket this launch writes
   const int* work_list;            // multi-GPU: this rank's positions of the range (range = indices into the list)
+  int n_ids;                       // number of nodes (dense ids are < n_ids)
   int init_mode;                   // GRank init (grank.h:64-83): every successor s contributes {s: +factor}; writes the current slot
 };
 
@@ -119,12 +120,26 @@ __device__ bool merge_node_seq(const MergeParams& P, const WarpTable<IdxT>& T, u
     const int s = table_find_or_insert(T, self_id, &nw);
     T.vals[s] = self0;
     T.list[0] = (IdxT)s;
-    *s_count = 1;
   }
+  int cnt = 1;  // distinct keys so far (warp-uniform); list[] holds their slots in first-touch order
   __syncwarp();
 
   unsigned long long merged = 0;
   bool overflow = false;
+  // one accumulate step, executed by all 32 lanes (k < 0: nothing to add): acc[k] = fma(x, mult, acc[k]); new keys are
+  // appended to the first-touch list with one ballot instead of a contended shared-memory counter
+  auto add_entry = [&](int k, double x) {
+    bool nw = false;
+    int s = 0;
+    if (k >= 0) {
+      s = table_find_or_insert(T, k, &nw);
+      const double a = nw ? 0.0 : T.vals[s];
+      T.vals[s] = fma(x, mult, a);  // grank.h:115 (mult = 1: exactly acc + x, mccompletepathv2.h:241)
+    }
+    const unsigned m = __ballot_sync(FULL, nw);
+    if (nw) T.list[cnt + __popc(m & ((1u << lane) - 1u))] = (IdxT)s;
+    cnt += __popc(m);
+  };
   for (long long eb = rb; eb < re && !overflow; eb += 32) {
     const int chunk = (int)((re - eb) < 32 ? (re - eb) : 32);
     const uint32_t mycol = (lane < chunk) ? P.g.col[eb + lane] : 0u;
@@ -134,60 +149,73 @@ __device__ bool merge_node_seq(const MergeParams& P, const WarpTable<IdxT>& T, u
       int k = -2 - lane;
       if (lane < chunk) k = (mycol & COL_SINK) ? (int)(mycol & ~COL_SINK) : P.g.label[mycol & COL_POS_MASK];
       const unsigned peers = __match_any_sync(FULL, k);
+      bool nw = false;
+      int s = 0;
       if (lane < chunk && (int)(__ffs(peers) - 1) == lane) {
-        bool nw;
-        const int s = table_find_or_insert(T, k, &nw);
+        s = table_find_or_insert(T, k, &nw);
         double a = nw ? 0.0 : T.vals[s];
         for (int r = __popc(peers); r > 0; r--) a += mult;
         T.vals[s] = a;
-        if (nw) { const int pos = atomicAdd(s_count, 1); T.list[pos] = (IdxT)s; }
       }
+      const unsigned m = __ballot_sync(FULL, nw);
+      if (nw) T.list[cnt + __popc(m & ((1u << lane) - 1u))] = (IdxT)s;
+      cnt += __popc(m);
       merged += (lane < chunk);
       __syncwarp();
-      if (*s_count > P.limit) { overflow = true; }
+      if (cnt > P.limit) { overflow = true; }
       continue;
     }
+    // successor baskets are fetched two steps ahead of the one being merged (lane g holds entries 4g..4g+3)
+    auto fetch = [&](int j, BasketFrag* fr) {
+      fr->id = make_int4(-1, -1, -1, -1);
+      fr->sa = fr->sb = make_double2(0.0, 0.0);
+      const uint32_t c = __shfl_sync(FULL, mycol, j < chunk ? j : 0);
+      if (j < chunk && !(c & COL_SINK) && lane < groups) {
+        const unsigned char* slot = P.buf[read_slot[(c >> COL_COLOUR_SHIFT) & 1u]] + (size_t)(c & COL_POS_MASK) * slot_bytes(Lp);
+        const int4* ids = reinterpret_cast<const int4*>(slot);
+        const double2* sc = reinterpret_cast<const double2*>(slot + (size_t)Lp * 4);
+        fr->id = __ldg(ids + lane);
+        fr->sa = __ldg(sc + lane);
+        fr->sb = __ldg(sc + (Lp >> 2) + lane);
+      }
+    };
+    BasketFrag f0, f1;
+    fetch(0, &f0);
+    fetch(1, &f1);
     for (int j = 0; j < chunk; j++) {
+      BasketFrag f2;
+      fetch(j + 2, &f2);
       const uint32_t c = __shfl_sync(FULL, mycol, j);
       if (c & COL_SINK) {
         // sink successor: its basket is the constant {s: 1-d} (GRank) / {s: 1} (MC)
-        if (lane == 0) {
-          const int k = (int)(c & ~COL_SINK);
-          const double x = (P.mode == MODE_GRANK) ? P.self_grank : 1.0;
-          bool nw;
-          const int s = table_find_or_insert(T, k, &nw);
-          const double a = nw ? 0.0 : T.vals[s];
-          T.vals[s] = fma(x, mult, a);
-          if (nw) { const int pos = (*s_count)++; T.list[pos] = (IdxT)s; }
-        }
+        add_entry(lane == 0 ? (int)(c & ~COL_SINK) : -1, (P.mode == MODE_GRANK) ? P.self_grank : 1.0);
         merged += (lane == 0);
       } else {
-        const unsigned int sp = c & COL_POS_MASK;
-        const int sc = (int)((c >> COL_COLOUR_SHIFT) & 1u);
-        const unsigned char* slot = P.buf[read_slot[sc]] + (size_t)sp * slot_bytes(Lp);
-        for (int g = lane; g < groups; g += 32) {
+        const unsigned char* slot = P.buf[read_slot[(c >> COL_COLOUR_SHIFT) & 1u]] + (size_t)(c & COL_POS_MASK) * slot_bytes(Lp);
+        for (int g0 = 0; g0 < groups; g0 += 32) {
           BasketFrag fr;
-          load_frag(slot, Lp, g, &fr);
+          if (g0 == 0) fr = f0;
+          else {
+            fr.id = make_int4(-1, -1, -1, -1);
+            fr.sa = fr.sb = make_double2(0.0, 0.0);
+            if (g0 + lane < groups) load_frag(slot, Lp, g0 + lane, &fr);
+          }
           const int ids[4] = {fr.id.x, fr.id.y, fr.id.z, fr.id.w};
           const double xs[4] = {fr.sa.x, fr.sa.y, fr.sb.x, fr.sb.y};
 #pragma unroll
           for (int e = 0; e < 4; e++) {
-            if (ids[e] >= 0) {
-              bool nw;
-              const int s = table_find_or_insert(T, ids[e], &nw);
-              const double a = nw ? 0.0 : T.vals[s];
-              T.vals[s] = fma(xs[e], mult, a);  // grank.h:115 (mult = 1: exactly acc + x, mccompletepathv2.h:241)
-              if (nw) { const int pos = atomicAdd(s_count, 1); T.list[pos] = (IdxT)s; }
-              merged++;
-            }
+            add_entry(ids[e], xs[e]);
+            merged += (ids[e] >= 0);
           }
         }
       }
       __syncwarp();
-      if (*s_count > P.limit) { overflow = true; break; }
+      if (cnt > P.limit) { overflow = true; break; }
+      f0 = f1;
+      f1 = f2;
     }
   }
-  const int n = *s_count;
+  const int n = cnt;
   __syncwarp();
   if (overflow) {
     for (int i = lane; i < n; i += 32) T.keys[T.list[i]] = KEY_EMPTY;
@@ -351,31 +379,35 @@ __global__ void __launch_bounds__(WARPS * 32) merge_seq_kernel(MergeParams P, un
 
   unsigned long long s_merged = 0, s_edges = 0, s_cands = 0, s_truncs = 0, s_ties = 0, s_bytes = 0, s_nodes = 0, s_requeue = 0;
   long long maxdiff = 0;
+  // nodes are fetched in small batches: thousands of tiny nodes hammering one global counter would serialise there
+  const unsigned int batch = (P.queue_in_idx >= 0 || CAP == 0) ? 1u : 4u;
   for (;;) {
-    unsigned int idx = 0;
-    if (lane == 0) idx = atomicAdd(&st->work[P.work_idx], 1u);
-    idx = __shfl_sync(FULL, idx, 0);
-    if (idx >= total) break;
+    unsigned int idx0 = 0;
+    if (lane == 0) idx0 = atomicAdd(&st->work[P.work_idx], batch);
+    idx0 = __shfl_sync(FULL, idx0, 0);
+    if (idx0 >= total) break;
     if (!table_clean) {
       for (unsigned int i = lane; i < cap; i += 32) T.keys[i] = KEY_EMPTY;
       __syncwarp();
       table_clean = true;
     }
-    const int p = (P.queue_in_idx >= 0) ? (int)P.queue_in[idx] : (P.work_list ? P.work_list[P.range_begin + (int)idx] : P.range_begin + (int)idx);
-    bool ok = false;
-    // class prediction: a node whose previous candidate count already exceeds this table goes straight on
-    const bool skip = P.queue_out != nullptr && P.ncand[p] > P.limit;
-    if (!skip)
-      ok = merge_node_seq<IdxT>(P, T, hist, s_count, p, write_slot, read_slot, s_merged, s_edges, s_cands, s_truncs,
-                                s_ties, s_bytes, maxdiff);
-    if (!ok) {
-      if (lane == 0) {
-        const unsigned int q = atomicAdd(&st->qcount[P.queue_out_idx], 1u);
-        P.queue_out[q] = (unsigned int)p;
-        s_requeue += skip ? 0 : 1;
+    for (unsigned int idx = idx0; idx < idx0 + batch && idx < total; idx++) {
+      const int p = (P.queue_in_idx >= 0) ? (int)P.queue_in[idx] : (P.work_list ? P.work_list[P.range_begin + (int)idx] : P.range_begin + (int)idx);
+      bool ok = false;
+      // class prediction: a node whose previous candidate count already exceeds this table goes straight on
+      const bool skip = P.queue_out != nullptr && P.ncand[p] > P.limit;
+      if (!skip)
+        ok = merge_node_seq<IdxT>(P, T, hist, s_count, p, write_slot, read_slot, s_merged, s_edges, s_cands, s_truncs,
+                                  s_ties, s_bytes, maxdiff);
+      if (!ok) {
+        if (lane == 0) {
+          const unsigned int q = atomicAdd(&st->qcount[P.queue_out_idx], 1u);
+          P.queue_out[q] = (unsigned int)p;
+          s_requeue += skip ? 0 : 1;
+        }
+      } else {
+        s_nodes += (lane == 0);
       }
-    } else {
-      s_nodes += (lane == 0);
     }
   }
   if (lane == 0) {

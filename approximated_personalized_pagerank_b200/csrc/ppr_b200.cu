@@ -272,7 +272,7 @@ static void session_free(pprb200_session* s) {
 }
 
 static int default_mid_deg() {
-  if (const char* e = getenv("PPRB200_MID_DEG")) return std::max(1, atoi(e));
+  if (const char* e = getenv("PPRB200_MID_DEG")) return std::min(PAR_MID_MAX, std::max(1, atoi(e)));
   return 64;
 }
 
@@ -354,7 +354,7 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
 
   // storage order: colour-major; inside a colour the exact-order class first, then the order-free class
   // (mid, big); every class by out-degree descending (ties by dense id) -- big nodes first for load balance
-  if (const char* e = getenv("PPRB200_CHUNK")) s->chunk = std::max(32, atoi(e));
+  if (const char* e = getenv("PPRB200_CHUNK")) s->chunk = std::min(PAR_CHUNK_MAX, std::max(32, atoi(e)));
   s->mid_deg = default_mid_deg();
   std::vector<int32_t> order;
   int cls_begin[2][3], cls_end[2][3];
@@ -599,16 +599,16 @@ static int enqueue_cascade(pprb200_session* s, MergeParams P, int range_begin, i
   return PPRB200_OK;
 }
 
-template <int H, int TCAP, int THREADS>
+template <int H, int TCAP, int CMAX, int COLCAP, int THREADS>
 static cudaError_t launch_par(pprb200_session* s, const ParParams& P, int grid) {
-  const size_t smem = par_smem_bytes<H, TCAP>();
+  const size_t smem = par_smem_bytes<H, TCAP, CMAX, COLCAP>() + 8 + par_queue_bytes(THREADS);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(merge_par_kernel<H, TCAP, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(merge_par_kernel<H, TCAP, CMAX, COLCAP, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  merge_par_kernel<H, TCAP, THREADS><<<grid, THREADS, smem, s->stream>>>(P);
+  merge_par_kernel<H, TCAP, CMAX, COLCAP, THREADS><<<grid, THREADS, smem, s->stream>>>(P);
   s->launch_count++;
   return cudaGetLastError();
 }
@@ -641,8 +641,8 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
     P.n_items = e - b;
     P.work_idx = 4 + cls;
     P.prof = s->d_prof ? s->d_prof + (size_t)cls * s->sm_count * 3 * 8 : nullptr;
-    cudaError_t err = cls == 1 ? launch_par<12288, 8192, 512>(s, P, std::min(s->sm_count, e - b))
-                               : launch_par<2048, 4096, 128>(s, P, std::min(s->sm_count * 3, e - b));
+    cudaError_t err = cls == 1 ? launch_par<8192, 4096, 6144, PAR_CHUNK_MAX, 512>(s, P, std::min(s->sm_count, e - b))
+                               : launch_par<2048, 2048, 2048, PAR_MID_MAX, 128>(s, P, std::min(s->sm_count * 3, e - b));
     if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_par launch failed: %s", cudaGetErrorString(err));
   }
   return PPRB200_OK;
@@ -723,6 +723,7 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
   P.ncand = s->d_ncand;
   P.peers = s->peers;
   P.work_list = s->d_seq_list;
+  P.n_ids = s->n;
   if (s->M > 0) {
     // init (grank.h:64-83)
     cudaMemsetAsync(s->d_ncand, 0, (size_t)s->M * sizeof(int), st);
@@ -807,7 +808,7 @@ static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t 
     P.g.row_off = s->d_row_off; P.g.col = s->d_col; P.g.label = s->d_label; P.g.dense_of = s->d_dense_of;
     P.buf[0] = s->d_buf[0]; P.buf[1] = s->d_buf[1];
     P.st = s->d_state;
-    P.M = s->M; P.src_begin = 0; P.src_end = s->M;
+    P.M = s->M; P.src_begin = 0; P.src_end = s->M; P.n_ids = s->n;
     P.colour = s->d_colour;
     P.peers = s->peers;
     P.Lp = Lp; P.L = (int)L; P.R = R; P.W = W; P.thresh = mc_coin_threshold(damping); P.seed = seed;
@@ -864,6 +865,7 @@ static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t 
   P.ncand = s->d_ncand;
   P.peers = s->peers;
   P.work_list = s->d_seq_list;
+  P.n_ids = s->n;
   if (s->M > 0 && rounds > 0) cudaMemsetAsync(s->d_ncand, 0, (size_t)s->M * sizeof(int), st);
   for (uint32_t r = 0; r < rounds; r++) {
     cudaEventRecord(s->ev_merge[2 * r], st);
