@@ -44,6 +44,17 @@ __global__ void state_reset_kernel(RunState* st) {
   }
 }
 
+// empty pool tables: the GSlot array at the start of each table gets key -1 / accumulator 0
+__global__ void pool_init_kernel(unsigned char* pool, size_t tbl_bytes, unsigned int cap, int n_tables) {
+  const size_t total = (size_t)cap * (size_t)n_tables;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    GSlot* g = reinterpret_cast<GSlot*>(pool + (i / cap) * tbl_bytes) + (i % cap);
+    g->key = KEY_EMPTY;
+    g->pad = 0;
+    g->acc = 0ull;
+  }
+}
+
 // end of an init / combine phase: clear cascade counters (and optionally the work statistics)
 __global__ void phase_end_kernel(RunState* st, int clear_stats, int flip_both, PeerDev peers, int barrier) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -183,9 +194,10 @@ struct pprb200_session {
   long long* d_item_off = nullptr;
   int* d_item_len = nullptr;
   unsigned char* d_pool = nullptr;
-  size_t tbl_bytes = 0;
-  unsigned int capmax = 0;
-  int n_tables = 0;
+  unsigned int tbl_cap[2] = {0, 0};   // [0 = mid, 1 = big] slots per pool table
+  int tbl_count_cls[2] = {0, 0};      // tables per class
+  int tbl_first[2] = {0, 0};          // first index into tbl_inuse / tbl_count
+  size_t pool_off[2] = {0, 0};        // byte offset of the class's tables in d_pool
   unsigned int* d_tbl_inuse = nullptr;
   unsigned int* d_tbl_count = nullptr;
   unsigned int* d_node_tbl = nullptr;
@@ -203,7 +215,7 @@ struct pprb200_session {
   unsigned char* d_colour = nullptr;
   unsigned char* d_buf[2] = {nullptr, nullptr};
   size_t buf_bytes = 0;
-  unsigned int* d_queue[3] = {nullptr, nullptr, nullptr};
+  unsigned int* d_queue[4] = {nullptr, nullptr, nullptr, nullptr};
   int* d_ncand = nullptr;
   RunState* d_state = nullptr;
   unsigned long long* d_final_stats = nullptr;
@@ -240,13 +252,39 @@ static int device_ok() {
   return PPRB200_OK;
 }
 
+// Device memory comes from the stream-ordered default pool with an unlimited release threshold: after the first call of
+// a process, allocating and freeing a session's buffers costs microseconds instead of cudaMalloc/cudaFree round trips
+// (the host-buffer entry points build and drop a session per call). Buffers that peers map through CUDA IPC must be
+// plain cudaMalloc allocations (`ipc` = true).
+static cudaStream_t g_alloc_stream = nullptr;
+
+static void pool_setup_once() {
+  static bool done = false;
+  if (done) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
+  done = true;
+}
+
 template <typename T>
-static int dev_alloc(T** p, size_t count) {
+static int dev_alloc(T** p, size_t count, bool ipc = false) {
   *p = nullptr;
   if (count == 0) count = 1;
-  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
-  if (e != cudaSuccess) return fail(PPRB200_ERR_ALLOC, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+  cudaError_t e = ipc ? cudaMalloc((void**)p, count * sizeof(T)) : cudaMallocAsync((void**)p, count * sizeof(T), g_alloc_stream);
+  if (e != cudaSuccess) return fail(PPRB200_ERR_ALLOC, "device allocation of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
   return PPRB200_OK;
+}
+
+static void dev_free(void* p, bool ipc = false) {
+  if (!p) return;
+  if (ipc) cudaFree(p);
+  else cudaFreeAsync(p, g_alloc_stream);
 }
 
 static void session_free(pprb200_session* s) {
@@ -254,17 +292,16 @@ static void session_free(pprb200_session* s) {
   for (int r = 0; r < MAX_WORLD; r++)
     for (int i = 0; i < 3; i++)
       if (s->ipc_opened[r][i]) cudaIpcCloseMemHandle(s->ipc_opened[r][i]);
-  cudaFree(s->d_mbox);
-  cudaFree(s->d_seq_list);
-  cudaFree(s->d_row_off); cudaFree(s->d_col); cudaFree(s->d_label); cudaFree(s->d_pos_of); cudaFree(s->d_dense_of); cudaFree(s->d_colour);
-  cudaFree(s->d_buf[0]); cudaFree(s->d_buf[1]);
-  for (int i = 0; i < 3; i++) cudaFree(s->d_queue[i]);
-  cudaFree(s->d_ncand); cudaFree(s->d_state); cudaFree(s->d_final_stats); cudaFree(s->d_ws);
-  cudaFree(s->d_out_ids); cudaFree(s->d_out_scores); cudaFree(s->d_out_cnt);
-  cudaFree(s->d_item_pos); cudaFree(s->d_item_off); cudaFree(s->d_item_len); cudaFree(s->d_pool);
-  cudaFree(s->d_walk_ws);
+  g_alloc_stream = s->stream;
+  const bool ipc = s->world > 1;
+  dev_free(s->d_mbox, ipc);
+  dev_free(s->d_buf[0], ipc); dev_free(s->d_buf[1], ipc);
+  void* plain[] = {s->d_seq_list, s->d_row_off, s->d_col, s->d_label, s->d_pos_of, s->d_dense_of, s->d_colour, s->d_queue[0], s->d_queue[1],
+                   s->d_queue[2], s->d_queue[3], s->d_ncand, s->d_state, s->d_final_stats, s->d_ws, s->d_out_ids, s->d_out_scores,
+                   s->d_out_cnt, s->d_item_pos, s->d_item_off, s->d_item_len, s->d_pool, s->d_walk_ws, s->d_prof, s->d_tbl_inuse,
+                   s->d_tbl_count, s->d_node_tbl, s->d_node_done};
+  for (void* q : plain) dev_free(q);
   for (int i = 0; i < 2; i++) if (s->ev_walk[i]) cudaEventDestroy(s->ev_walk[i]);
-  cudaFree(s->d_prof); cudaFree(s->d_tbl_inuse); cudaFree(s->d_tbl_count); cudaFree(s->d_node_tbl); cudaFree(s->d_node_done);
   if (s->ev_begin) cudaEventDestroy(s->ev_begin);
   if (s->ev_end) cudaEventDestroy(s->ev_end);
   for (auto e : s->ev_merge) cudaEventDestroy(e);
@@ -333,6 +370,8 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   pprb200_session* s = new pprb200_session();
   std::memset(&s->peers, 0, sizeof(s->peers));
   std::memset(s->ipc_opened, 0, sizeof(s->ipc_opened));
+  pool_setup_once();
+  g_alloc_stream = (cudaStream_t)stream;
   s->n = n;
   s->max_L = max_L;
   s->hub_threshold = hub_threshold == 0 ? PPRB200_DEFAULT_HUB_THRESHOLD : hub_threshold;
@@ -432,9 +471,9 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   s->buf_bytes = (size_t)std::max(M, 1) * slot_bytes(Lp);
   if ((rc = dev_alloc(&s->d_row_off, (size_t)M + 1)) || (rc = dev_alloc(&s->d_col, (size_t)E)) ||
       (rc = dev_alloc(&s->d_label, (size_t)M)) || (rc = dev_alloc(&s->d_pos_of, (size_t)n)) || (rc = dev_alloc(&s->d_dense_of, (size_t)n)) ||
-      (rc = dev_alloc(&s->d_colour, (size_t)n)) || (rc = dev_alloc(&s->d_buf[0], s->buf_bytes)) ||
-      (rc = dev_alloc(&s->d_buf[1], s->buf_bytes)) || (rc = dev_alloc(&s->d_queue[0], (size_t)M)) ||
-      (rc = dev_alloc(&s->d_queue[1], (size_t)M)) || (rc = dev_alloc(&s->d_queue[2], (size_t)M)) ||
+      (rc = dev_alloc(&s->d_colour, (size_t)n)) || (rc = dev_alloc(&s->d_buf[0], s->buf_bytes, world > 1)) ||
+      (rc = dev_alloc(&s->d_buf[1], s->buf_bytes, world > 1)) || (rc = dev_alloc(&s->d_queue[0], (size_t)M)) ||
+      (rc = dev_alloc(&s->d_queue[1], (size_t)M)) || (rc = dev_alloc(&s->d_queue[2], (size_t)M)) || (rc = dev_alloc(&s->d_queue[3], (size_t)M)) ||
       (rc = dev_alloc(&s->d_ncand, (size_t)M)) || (rc = dev_alloc(&s->d_state, 1)) ||
       (rc = dev_alloc(&s->d_final_stats, 2))) {
     session_free(s);
@@ -459,17 +498,29 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
     if (!seq_list.empty()) UP(s->d_seq_list, seq_list.data(), seq_list.size() * sizeof(int));
   }
   if (s->n_items > 0) {
+    // global-table pool of the order-free path: one table per CTA that can be in flight, sized for the worst case of
+    // its class (big: the largest hub; mid: out-degree <= mid_deg) so that an acquired table can never overflow
     const int Lpm = roundup4((int)max_L);
-    const unsigned long long worst = std::min<unsigned long long>(2ull * ((unsigned long long)s->max_deg_par * Lpm + 2ull),
-                                                                  2ull * ((unsigned long long)n + 1ull));
-    unsigned int cap = 1024;
-    while ((unsigned long long)cap < worst) cap <<= 1;
-    s->capmax = cap;
-    s->n_tables = s->sm_count * 3 + 8;  // >= CTAs in flight of either merge_par instantiation
-    s->tbl_bytes = (size_t)cap * (sizeof(GSlot) + sizeof(unsigned int) + 4 + 2);  // slots, slot list, compact scores (cap/2 x 8), labels (cap/2 x 4)
+    auto pow2cap = [&](unsigned long long deg) {
+      const unsigned long long worst = std::min<unsigned long long>(2ull * (deg * Lpm + 2ull), 2ull * ((unsigned long long)n + 1ull));
+      unsigned int cap = 1024;
+      while ((unsigned long long)cap < worst) cap <<= 1;
+      return cap;
+    };
+    const unsigned long long per_slot = sizeof(GSlot) + sizeof(unsigned int) + 4 + 2;  // slot, list entry, compact score (cap/2 x 8), label (cap/2 x 4)
+    s->tbl_cap[1] = pow2cap((unsigned long long)s->max_deg_par);
+    s->tbl_cap[0] = std::min(s->tbl_cap[1], pow2cap((unsigned long long)s->mid_deg));
+    s->tbl_count_cls[1] = s->sm_count + 8;      // >= CTAs in flight of the big instantiation
+    s->tbl_count_cls[0] = s->sm_count * 3 + 8;  // ... of the mid instantiation
+    s->tbl_first[1] = 0;
+    s->tbl_first[0] = s->tbl_count_cls[1];
+    s->pool_off[1] = 0;
+    s->pool_off[0] = (size_t)s->tbl_count_cls[1] * s->tbl_cap[1] * per_slot;
+    const size_t pool_bytes = s->pool_off[0] + (size_t)s->tbl_count_cls[0] * s->tbl_cap[0] * per_slot;
+    const int n_tables = s->tbl_count_cls[0] + s->tbl_count_cls[1];
     if ((rc = dev_alloc(&s->d_item_pos, (size_t)s->n_items)) || (rc = dev_alloc(&s->d_item_off, (size_t)s->n_items)) ||
-        (rc = dev_alloc(&s->d_item_len, (size_t)s->n_items)) || (rc = dev_alloc(&s->d_pool, s->tbl_bytes * (size_t)s->n_tables)) ||
-        (rc = dev_alloc(&s->d_tbl_inuse, (size_t)s->n_tables)) || (rc = dev_alloc(&s->d_tbl_count, (size_t)s->n_tables)) ||
+        (rc = dev_alloc(&s->d_item_len, (size_t)s->n_items)) || (rc = dev_alloc(&s->d_pool, pool_bytes)) ||
+        (rc = dev_alloc(&s->d_tbl_inuse, (size_t)n_tables)) || (rc = dev_alloc(&s->d_tbl_count, (size_t)n_tables)) ||
         (rc = dev_alloc(&s->d_node_tbl, (size_t)M)) || (rc = dev_alloc(&s->d_node_done, (size_t)M))) {
       session_free(s);
       return rc;
@@ -477,22 +528,19 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
     UP(s->d_item_pos, item_pos.data(), (size_t)s->n_items * sizeof(int));
     UP(s->d_item_off, item_off.data(), (size_t)s->n_items * sizeof(long long));
     UP(s->d_item_len, item_len.data(), (size_t)s->n_items * sizeof(int));
-    cudaMemsetAsync(s->d_tbl_inuse, 0, (size_t)s->n_tables * sizeof(unsigned int), st);
-    cudaMemsetAsync(s->d_tbl_count, 0, (size_t)s->n_tables * sizeof(unsigned int), st);
+    cudaMemsetAsync(s->d_tbl_inuse, 0, (size_t)n_tables * sizeof(unsigned int), st);
+    cudaMemsetAsync(s->d_tbl_count, 0, (size_t)n_tables * sizeof(unsigned int), st);
     cudaMemsetAsync(s->d_node_tbl, 0, (size_t)M * sizeof(unsigned int), st);
     cudaMemsetAsync(s->d_node_done, 0, (size_t)M * sizeof(unsigned int), st);
-    // pool tables: keys -1 / acc 0. GSlot = {key, pad, acc}: fill with 0xff then zero the acc words
-    for (int t = 0; t < s->n_tables; t++) {
-      unsigned char* base = s->d_pool + (size_t)t * s->tbl_bytes;
-      cudaMemset2DAsync(base, sizeof(GSlot), 0xff, 8, cap, st);
-      cudaMemset2DAsync(base + 8, sizeof(GSlot), 0x00, 8, cap, st);
-    }
+    for (int cls = 0; cls < 2; cls++)  // pool tables start empty: keys -1, accumulators 0
+      pool_init_kernel<<<s->sm_count * 8, 256, 0, st>>>(s->d_pool + s->pool_off[cls], (size_t)s->tbl_cap[cls] * per_slot, s->tbl_cap[cls],
+                                                        s->tbl_count_cls[cls]);
   }
 #undef UP
   cudaError_t e = cudaStreamSynchronize(st);  // host vectors go out of scope
   if (e != cudaSuccess) { session_free(s); return fail(PPRB200_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e)); }
   cudaMemsetAsync(s->d_ncand, 0, (size_t)std::max(M, 1) * sizeof(int), st);
-  if ((rc = dev_alloc(&s->d_mbox, (size_t)2 * MAX_WORLD))) { session_free(s); return rc; }
+  if ((rc = dev_alloc(&s->d_mbox, (size_t)2 * MAX_WORLD, world > 1))) { session_free(s); return rc; }
   cudaMemsetAsync(s->d_mbox, 0, sizeof(Mailbox) * 2 * MAX_WORLD, st);
   cudaMemsetAsync(s->d_state, 0, sizeof(RunState), st);
   cudaEventCreate(&s->ev_begin);
@@ -500,8 +548,8 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   cudaEventCreate(&s->ev_walk[0]);
   cudaEventCreate(&s->ev_walk[1]);
   if (getenv("PPRB200_PROF")) {
-    if ((rc = dev_alloc(&s->d_prof, (size_t)2 * s->sm_count * 3 * 8))) { session_free(s); return rc; }
-    cudaMemsetAsync(s->d_prof, 0, (size_t)2 * s->sm_count * 3 * 8 * sizeof(unsigned long long), st);
+    if ((rc = dev_alloc(&s->d_prof, (size_t)2 * s->sm_count * 8 * 8))) { session_free(s); return rc; }
+    cudaMemsetAsync(s->d_prof, 0, (size_t)2 * s->sm_count * 8 * 8 * sizeof(unsigned long long), st);
   }
   s->h2d_ms = now_ms() - t1;
   *out = s;
@@ -586,7 +634,7 @@ static int enqueue_cascade(pprb200_session* s, MergeParams P, int range_begin, i
     int grid = std::max(1, gw / warps_g);
     const size_t need = (size_t)grid * warps_g * region;
     if (need > s->ws_bytes) {
-      cudaFree(s->d_ws);
+      dev_free(s->d_ws);
       s->d_ws = nullptr;
       s->ws_bytes = 0;
       int rc = dev_alloc(&s->d_ws, need);
@@ -623,12 +671,6 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
   P.M.L = L;
   P.M.colour = c;
   P.chunk = s->chunk;
-  P.pool = s->d_pool;
-  P.tbl_bytes = s->tbl_bytes;
-  P.capmax = s->capmax;
-  P.n_tables = s->n_tables;
-  P.tbl_inuse = s->d_tbl_inuse;
-  P.tbl_count = s->d_tbl_count;
   P.node_tbl = s->d_node_tbl;
   P.node_done = s->d_node_done;
   P.n_ids = s->n;
@@ -640,7 +682,13 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
     P.item_len = s->d_item_len + b;
     P.n_items = e - b;
     P.work_idx = 4 + cls;
-    P.prof = s->d_prof ? s->d_prof + (size_t)cls * s->sm_count * 3 * 8 : nullptr;
+    P.pool = s->d_pool + s->pool_off[cls];
+    P.capmax = s->tbl_cap[cls];
+    P.tbl_bytes = (size_t)s->tbl_cap[cls] * (sizeof(GSlot) + sizeof(unsigned int) + 4 + 2);
+    P.n_tables = s->tbl_count_cls[cls];
+    P.tbl_inuse = s->d_tbl_inuse + s->tbl_first[cls];
+    P.tbl_count = s->d_tbl_count + s->tbl_first[cls];
+    P.prof = s->d_prof ? s->d_prof + (size_t)cls * s->sm_count * 8 * 8 : nullptr;
     cudaError_t err = cls == 1 ? launch_par<8192, 4096, 6144, PAR_CHUNK_MAX, 512>(s, P, std::min(s->sm_count, e - b))
                                : launch_par<2048, 2048, 2048, PAR_MID_MAX, 128>(s, P, std::min(s->sm_count * 3, e - b));
     if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_par launch failed: %s", cudaGetErrorString(err));
@@ -651,7 +699,7 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
 static int ensure_outputs(pprb200_session* s, uint32_t K) {
   const size_t need = (size_t)std::max(s->n, 1) * K;
   if (need > s->out_capacity) {
-    cudaFree(s->d_out_ids); cudaFree(s->d_out_scores);
+    dev_free(s->d_out_ids); dev_free(s->d_out_scores);
     s->d_out_ids = nullptr; s->d_out_scores = nullptr; s->out_capacity = 0;
     int rc;
     if ((rc = dev_alloc(&s->d_out_ids, need)) || (rc = dev_alloc(&s->d_out_scores, need))) return rc;
@@ -697,6 +745,7 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
   if (rc) return rc;
   if (L > s->max_L) return fail(PPRB200_ERR_PARAM, "L=%u exceeds the session's max_L=%u", L, s->max_L);
   if ((size_t)roundup4((int)L) * 12 > 200 * 1024) return fail(PPRB200_ERR_PARAM, "L=%u is above this build's limit of 17064", L);
+  g_alloc_stream = s->stream;
   if ((rc = ensure_outputs(s, K))) return rc;
   if (s->world > 1 && !s->attached) return fail(PPRB200_ERR_STATE, "world=%d session: call pprb200_session_ipc_attach before running", s->world);
   s->last_mode = MODE_GRANK;
@@ -784,6 +833,7 @@ static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t 
   if (rc) return rc;
   if (L > s->max_L) return fail(PPRB200_ERR_PARAM, "L=%u exceeds the session's max_L=%u", L, s->max_L);
   if ((size_t)roundup4((int)L) * 12 > 200 * 1024) return fail(PPRB200_ERR_PARAM, "L=%u is above this build's limit of 17064", L);
+  g_alloc_stream = s->stream;
   if ((rc = ensure_outputs(s, K))) return rc;
   if (s->world > 1 && !s->attached) return fail(PPRB200_ERR_STATE, "world=%d session: call pprb200_session_ipc_attach before running", s->world);
   s->last_mode = MODE_MC;
@@ -836,7 +886,7 @@ static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t 
       const size_t per = (size_t)cap * sizeof(WalkSlot);
       const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)s->sm_count, ((size_t)2 << 30) / per));
       if ((size_t)grid * per > s->walk_ws_bytes) {
-        cudaFree(s->d_walk_ws);
+        dev_free(s->d_walk_ws);
         s->d_walk_ws = nullptr; s->walk_ws_bytes = 0;
         if ((rc = dev_alloc(&s->d_walk_ws, (size_t)grid * cap))) return rc;
         s->walk_ws_bytes = (size_t)grid * per;
@@ -1022,10 +1072,10 @@ int pprb200_session_kernel_time(pprb200_session* s, int which, uint32_t* launche
 int pprb200_debug_prof(pprb200_session* s, unsigned long long* out, int* n_ctas) {
   if (!s || !s->d_prof) return fail(PPRB200_ERR_STATE, "profiling counters not enabled (PPRB200_PROF=1)");
   cudaStreamSynchronize(s->stream);
-  const size_t cnt = (size_t)2 * s->sm_count * 3 * 8;
+  const size_t cnt = (size_t)2 * s->sm_count * 8 * 8;
   cudaMemcpy(out, s->d_prof, cnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   cudaMemset(s->d_prof, 0, cnt * sizeof(unsigned long long));
-  if (n_ctas) *n_ctas = s->sm_count * 3;
+  if (n_ctas) *n_ctas = s->sm_count * 8;
   return PPRB200_OK;
 }
 

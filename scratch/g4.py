@@ -12,9 +12,9 @@ for rep in range(2):
     s.grank(50,100,iters,0.85,-1.0)
     st=s.stats(); l,ms=s.kernel_time(0)
     print(f"rmat{scale} hub>{hub}: kernel_ms {st['kernel_ms']:.2f} merge_ms {ms:.2f} alg GB/s {st['algorithmic_bytes']/ms/1e6:.1f} requeues {st['overflow_requeues']}")
-    buf=np.zeros(2*148*3*8,dtype=np.uint64); n=C.c_int(0)
+    buf=np.zeros(2*148*8*8,dtype=np.uint64); n=C.c_int(0)
     lib.pprb200_debug_prof(s.handle, buf.ctypes.data_as(C.c_void_p), C.byref(n))
-    buf=buf.reshape(2,148*3,8)
+    buf=buf.reshape(2,148*8,8)
     for cls,nm in ((1,'big'),(0,'mid')):
         b=buf[cls].astype(np.float64); tot=b.sum(1); act=tot>0
         print(f"  {nm}: CTAs {act.sum()} total cyc/CTA mean {tot[act].mean():.3e} max {tot[act].max():.3e}")
