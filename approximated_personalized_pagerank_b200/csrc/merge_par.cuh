@@ -43,6 +43,7 @@ struct ParParams {
   unsigned int* node_tbl;      // [M] 0 none, 1 being acquired, else table index + 2
   unsigned int* node_done;     // [M] chunks completed
   int n_ids;                   // label space (identity hashing when the table covers it)
+  int use_sketch;              // two-pass merge with the tail sketch for single-item nodes
   unsigned long long* prof;    // optional [gridDim.x * 8] phase cycle counters (PPRB200_PROF=1)
 };
 
@@ -229,12 +230,13 @@ __device__ __forceinline__ void fixed_add_shared(uint2* word, unsigned long long
   if (hi) atomicAdd(&word->y, hi);
 }
 
-constexpr int PAR_CHUNK_MAX = 1024;  // successors per work item of the big class (column words are staged in shared memory)
+constexpr int PAR_CHUNK_MAX = 1024;  // column words of the big class are staged in shared memory in tiles of this many successors
 constexpr int PAR_MID_MAX = 128;     // largest out-degree the mid class may be configured for
 
-template <int H, int TCAP, int CMAX, int COLCAP>
+template <int H, int TCAP, int CMAX, int COLCAP, int R>
 constexpr size_t par_smem_bytes() {
-  return (size_t)H * 8 + (size_t)TCAP * 14 + (size_t)H / 8 + (size_t)CMAX * 12 + (size_t)COLCAP * 4 + sizeof(ParShared);
+  return (size_t)H * 8 + (size_t)TCAP * 14 + (size_t)H / 8 + (size_t)CMAX * 12 + (size_t)COLCAP * 4 + (size_t)R * 8 + (size_t)R / 4 +
+         sizeof(ParShared);
 }
 constexpr size_t par_queue_bytes(int threads) { return (size_t)(threads / 32) * 64 * 12; }
 
@@ -249,8 +251,17 @@ __device__ __forceinline__ void load_frag_all(const unsigned char* slot, int Lp,
 }
 
 // H dense labels, TCAP tail slots (TLIMIT distinct tail keys admitted; concurrent inserts may overshoot by < THREADS),
-// CMAX compact candidates, COLCAP staged column words (>= successors per work item), THREADS threads.
-template <int H, int TCAP, int CMAX, int COLCAP, int THREADS>
+// CMAX compact candidates, COLCAP staged column words per tile, R sketch buckets (0: single-pass only), THREADS threads.
+//
+// Two-pass merge of a single-item node (R > 0): most of a hub's candidates are tail labels that receive one or two tiny
+// contributions and can never reach the top-L, yet hashing them costs far more than the dense labels that decide the
+// result. Pass 1 adds dense labels exactly and tail labels into a count-min style sketch (bucket = hash(label), same
+// fixed point): a bucket sum bounds every label in it from above. The L-th largest dense score tau bounds the final
+// threshold from below (adding candidates can only raise it), so a tail label whose bucket sums to less than tau is out
+// -- strictly, ties included. Pass 2 re-reads the baskets and accumulates exactly only the tail labels of surviving
+// buckets. Everything stays in shared memory; the result is the same set of sums the single pass produces for every
+// candidate that can be selected.
+template <int H, int TCAP, int CMAX, int COLCAP, int R, int THREADS>
 __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
   constexpr int TLIMIT = TCAP * 13 / 16 - THREADS;
   constexpr int NW = THREADS / 32;
@@ -262,10 +273,14 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
   unsigned char* sp = smem;
   uint2* s_dense = reinterpret_cast<uint2*>(sp); sp += (size_t)H * 8;
   uint2* t_acc = reinterpret_cast<uint2*>(sp); sp += (size_t)TCAP * 8;
+  static_assert(((size_t)COLCAP * 4) % 8 == 0 && ((size_t)R / 8) % 4 == 0, "shared-memory carve-up alignment");
   unsigned long long* c_bits = reinterpret_cast<unsigned long long*>(sp); sp += (size_t)CMAX * 8;  // compact candidates: score bits
   int* t_keys = reinterpret_cast<int*>(sp); sp += (size_t)TCAP * 4;
   int* c_id = reinterpret_cast<int*>(sp); sp += (size_t)CMAX * 4;                                   //                     labels
   uint32_t* s_col = reinterpret_cast<uint32_t*>(sp); sp += (size_t)COLCAP * 4;
+  uint2* s_sk = reinterpret_cast<uint2*>(sp); sp += (size_t)R * 8;                     // sketch buckets (fixed point)
+  unsigned int* s_alive = reinterpret_cast<unsigned int*>(sp); sp += (size_t)R / 8;    // buckets that may hold a top-L label
+  unsigned int* s_pre = reinterpret_cast<unsigned int*>(sp); sp += (size_t)R / 8;      // buckets of the old basket's tail labels
   unsigned int* s_zbits = reinterpret_cast<unsigned int*>(sp); sp += (size_t)H / 8;  // dense labels touched with a 0 word
   unsigned short* t_list = reinterpret_cast<unsigned short*>(sp); sp += (size_t)TCAP * 2;
   ParShared* S = reinterpret_cast<ParShared*>(sp); sp += (sizeof(ParShared) + 7) & ~(size_t)7;
@@ -332,9 +347,6 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
     const double fscale = f * scale;
     const double self0 = (M.mode == MODE_GRANK) ? M.self_grank : 1.0;
     const int write_slot = init_mode ? st->slot[M.colour] : (st->slot[M.colour] ^ 1);
-
-    // stage the chunk's column words (coalesced) so that the basket prefetch below never waits on them
-    for (int j = tid; j < clen; j += THREADS) s_col[j] = M.g.col[cb + j];
 
     // lazily bound global table of this node (acquired by the first CTA that needs it)
     GSlot* gslots = nullptr;
@@ -403,32 +415,17 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
         else S->spilled = 1;
       }
     };
-    auto accumulate = [&](bool spill_ok) {
+    // pass 0: single pass (dense + tail table, spilling to the node's global table when `spill_ok`)
+    // pass 1: dense labels exactly, tail labels into the sketch          (R > 0, single-item nodes)
+    // pass 2: tail labels of surviving buckets exactly into the tail table
+    auto accumulate = [&](int pass, bool spill_ok) {
       merged = 0;
-      if (init_mode) {
-        // grank.h:79-80: every occurrence of a successor adds `factor`; here: multiplicity += 1
-        for (int j = tid; j < clen; j += THREADS) {
-          const uint32_t c = s_col[j];
-          const int k = (c & COL_SINK) ? (int)(c & ~COL_SINK) : M.g.label[c & COL_POS_MASK];
-          if ((unsigned)k < (unsigned)H) fixed_add_shared(&s_dense[k], 1ull);
-          else slow_contribute(k, 1ull, spill_ok);
-          merged++;
-        }
-        return;
-      }
-      // warp w merges successors w, w+NW, ... with the next two baskets already in flight
+      bool tail_seen = false;
+      // warp w merges successors w, w+NW, ... of a tile with the next two baskets already in flight
       auto slot_of = [&](uint32_t cc) -> const unsigned char* {
         return M.buf[read_slot[(cc >> COL_COLOUR_SHIFT) & 1u]] + (size_t)(cc & COL_POS_MASK) * slot_bytes(Lp);
       };
-      auto fetch = [&](int j, BasketFrag* fr) {
-        fr->id = make_int4(-1, -1, -1, -1);
-        fr->sa = fr->sb = make_double2(0.0, 0.0);
-        if (j < clen) {
-          const uint32_t cc = s_col[j];
-          if (!(cc & COL_SINK) && lane < groups) load_frag_all(slot_of(cc), Lp, lane, fr);
-        }
-      };
-      // Entries that miss the dense range (tail labels, zero products) are rare but slow (hash probe, CAS); taken
+      // Entries that miss the fast paths (tail labels, zero products) are rare but slow (hash probe, CAS); taken
       // inline they would stall the whole warp behind two or three lanes. They are parked in a per-warp queue and
       // drained 32 at a time with every lane busy.
       int qn = 0;
@@ -452,9 +449,26 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
         __syncwarp();
       };
       auto contribute = [&](int k, unsigned long long xf) {  // called by all 32 lanes; k < 0: nothing
-        const bool fast = (unsigned)k < (unsigned)H && xf != 0ull;
-        if (fast) fixed_add_shared(&s_dense[k], xf);
-        const bool slow = !fast && k >= 0;
+        const bool dense = (unsigned)k < (unsigned)H;
+        bool slow;
+        if (pass == 2) {
+          slow = false;
+          if (k >= H) {
+            const unsigned int b = hash_key(k) & (unsigned)(R > 0 ? R - 1 : 0);
+            slow = (s_alive[b >> 5] >> (b & 31)) & 1u;
+          }
+        } else {
+          const bool fast = dense && xf != 0ull;
+          if (fast) fixed_add_shared(&s_dense[k], xf);
+          if (pass == 1 && k >= H) {
+            tail_seen = true;
+            const unsigned int b = hash_key(k) & (unsigned)(R > 0 ? R - 1 : 0);
+            if (xf) fixed_add_shared(&s_sk[b], xf);
+            slow = (s_pre[b >> 5] >> (b & 31)) & 1u;  // bucket of an old-basket label: accumulate exactly right away
+          } else {
+            slow = !fast && k >= 0;
+          }
+        }
         const unsigned m = __ballot_sync(FULL, slow);
         if (m) {
           if (slow) { const int pos = qn + __popc(m & ((1u << lane) - 1u)); qk[pos] = k; qv[pos] = xf; }
@@ -462,39 +476,66 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
           if (qn >= 32) drain(32);
         }
       };
-      BasketFrag f0, f1;
-      fetch(w, &f0);
-      fetch(w + NW, &f1);
-      for (int j = w; j < clen; j += NW) {
-        BasketFrag f2;
-        fetch(j + 2 * NW, &f2);
-        const uint32_t c = s_col[j];
-        if (c & COL_SINK) {
-          const double x = (M.mode == MODE_GRANK) ? M.self_grank : 1.0;
-          contribute(lane == 0 ? (int)(c & ~COL_SINK) : -1, (unsigned long long)__double2ll_rn(x * fscale));
-          merged += (lane == 0);
-        } else {
-          for (int g0 = 0; g0 < groups; g0 += 32) {
-            BasketFrag fr;
-            if (g0 == 0) fr = f0;
-            else {
-              fr.id = make_int4(-1, -1, -1, -1);
-              fr.sa = fr.sb = make_double2(0.0, 0.0);
-              if (g0 + lane < groups) load_frag_all(slot_of(c), Lp, g0 + lane, &fr);
-            }
-            const int ids[4] = {fr.id.x, fr.id.y, fr.id.z, fr.id.w};
-            const double xs[4] = {fr.sa.x, fr.sa.y, fr.sb.x, fr.sb.y};
+      for (int t0 = 0; t0 < clen; t0 += COLCAP) {
+        const int tlen = clen - t0 < COLCAP ? clen - t0 : COLCAP;
+        __syncthreads();
+        // stage the tile's column words (coalesced) so that the basket prefetch below never waits on them
+        for (int j = tid; j < tlen; j += THREADS) s_col[j] = M.g.col[cb + t0 + j];
+        __syncthreads();
+        if (init_mode) {
+          // grank.h:79-80: every occurrence of a successor adds `factor`; here: multiplicity += 1
+          for (int j = tid; j < tlen; j += THREADS) {
+            const uint32_t c = s_col[j];
+            const int k = (c & COL_SINK) ? (int)(c & ~COL_SINK) : M.g.label[c & COL_POS_MASK];
+            if ((unsigned)k < (unsigned)H) fixed_add_shared(&s_dense[k], 1ull);
+            else slow_contribute(k, 1ull, spill_ok);
+            merged++;
+          }
+          continue;
+        }
+        auto fetch = [&](int j, BasketFrag* fr) {
+          fr->id = make_int4(-1, -1, -1, -1);
+          fr->sa = fr->sb = make_double2(0.0, 0.0);
+          if (j < tlen) {
+            const uint32_t cc = s_col[j];
+            if (!(cc & COL_SINK) && lane < groups) load_frag_all(slot_of(cc), Lp, lane, fr);
+          }
+        };
+        BasketFrag f0, f1;
+        fetch(w, &f0);
+        fetch(w + NW, &f1);
+        for (int j = w; j < tlen; j += NW) {
+          BasketFrag f2;
+          fetch(j + 2 * NW, &f2);
+          const uint32_t c = s_col[j];
+          if (c & COL_SINK) {
+            const double x = (M.mode == MODE_GRANK) ? M.self_grank : 1.0;
+            contribute(lane == 0 ? (int)(c & ~COL_SINK) : -1, (unsigned long long)__double2ll_rn(x * fscale));
+            merged += (lane == 0);
+          } else {
+            for (int g0 = 0; g0 < groups; g0 += 32) {
+              BasketFrag fr;
+              if (g0 == 0) fr = f0;
+              else {
+                fr.id = make_int4(-1, -1, -1, -1);
+                fr.sa = fr.sb = make_double2(0.0, 0.0);
+                if (g0 + lane < groups) load_frag_all(slot_of(c), Lp, g0 + lane, &fr);
+              }
+              const int ids[4] = {fr.id.x, fr.id.y, fr.id.z, fr.id.w};
+              const double xs[4] = {fr.sa.x, fr.sa.y, fr.sb.x, fr.sb.y};
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-              contribute(ids[e], (unsigned long long)__double2ll_rn(xs[e] * fscale));
-              merged += (ids[e] >= 0);
+              for (int e = 0; e < 4; e++) {
+                contribute(ids[e], (unsigned long long)__double2ll_rn(xs[e] * fscale));
+                merged += (ids[e] >= 0);
+              }
             }
           }
+          f0 = f1;
+          f1 = f2;
         }
-        f0 = f1;
-        f1 = f2;
       }
       if (qn > 0) drain(qn);
+      return tail_seen;
     };
     auto reset_shared = [&]() {  // drop the partial sums of this item
       __syncthreads();
@@ -509,70 +550,178 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
       __syncthreads();
       if (tid == 0) { S->tcount = 0; S->spilled = 0; s_requeue++; }
     };
-    // a node expected to outgrow the shared-memory structures binds its global table up front
-    if (S->table < 0 && M.ncand[p] > (TLIMIT + H / 2 < CMAX ? TLIMIT + H / 2 : CMAX)) bind_table();
-    PROF_MARK(1);
-    accumulate(S->table >= 0);
-    __syncthreads();
-    PROF_MARK(2);
-
-    // single-chunk node that stayed in shared memory: compact the candidates (score bits, label)
-    int n = 0;
-    if (S->table < 0 && !S->spilled) {
-      if (tid == 0) S->ncand = 0;
-      __syncthreads();
-      const double base_self = init_mode ? M.self_grank : 0.0;
-      for (int i0 = 0; i0 < H; i0 += THREADS) {
-        const int i = i0 + tid;
-        const uint2 a = s_dense[i];
-        const bool ok = dense_touched(i, a);
-        const unsigned m = __ballot_sync(FULL, ok);
-        if (m) {
-          int basep = 0;
-          if (lane == (int)(__ffs(m) - 1)) basep = atomicAdd(&S->ncand, __popc(m));
-          basep = __shfl_sync(FULL, basep, __ffs(m) - 1);
+    // compaction of the candidates held in shared memory into (score bits, label) arrays; `from_dense` / `from_tail`
+    // select the sources, positions continue from S->ncand
+    const double base_self = init_mode ? M.self_grank : 0.0;
+    bool dropped_local = false;  // this thread left a candidate out of the compact arrays (below the lower bound)
+    auto compact = [&](bool from_dense, bool from_tail, int tail_from, unsigned long long theta) {
+      if (from_dense)
+        for (int i0 = 0; i0 < H; i0 += THREADS) {
+          const int i = i0 + tid;
+          const uint2 a = s_dense[i];
+          bool ok = dense_touched(i, a);
+          unsigned long long bits = 0ull;
           if (ok) {
-            const int pos = basep + __popc(m & ((1u << lane) - 1u));
-            if (pos < CMAX) {
-              const double v = par_score(((unsigned long long)a.y << 32) | a.x, init_mode, inv, mult, (init_mode && i == self_id) ? base_self : 0.0);
-              c_bits[pos] = (unsigned long long)__double_as_longlong(v);
-              c_id[pos] = i;
+            bits = (unsigned long long)__double_as_longlong(
+                par_score(((unsigned long long)a.y << 32) | a.x, init_mode, inv, mult, (init_mode && i == self_id) ? base_self : 0.0));
+            ok = bits >= theta;  // below the lower bound of the cut: cannot be kept
+            dropped_local |= !ok;
+          }
+          const unsigned m = __ballot_sync(FULL, ok);
+          if (m) {
+            int basep = 0;
+            if (lane == (int)(__ffs(m) - 1)) basep = atomicAdd(&S->ncand, __popc(m));
+            basep = __shfl_sync(FULL, basep, __ffs(m) - 1);
+            if (ok) {
+              const int pos = basep + __popc(m & ((1u << lane) - 1u));
+              if (pos < CMAX) { c_bits[pos] = bits; c_id[pos] = i; }
+            }
+          }
+        }
+      if (from_tail) {
+        const int nt0 = S->tcount;
+        for (int i0 = tail_from; i0 < nt0; i0 += THREADS) {
+          const int i = i0 + tid;
+          bool ok = i < nt0;
+          unsigned long long bits = 0ull;
+          int id = 0;
+          if (ok) {
+            const int sl = t_list[i];
+            id = t_keys[sl];
+            bits = (unsigned long long)__double_as_longlong(par_score(((unsigned long long)t_acc[sl].y << 32) | t_acc[sl].x, init_mode, inv,
+                                                                      mult, (init_mode && id == self_id) ? base_self : 0.0));
+            ok = bits >= theta;
+            dropped_local |= !ok;
+          }
+          const unsigned m = __ballot_sync(FULL, ok);
+          if (m) {
+            int basep = 0;
+            if (lane == (int)(__ffs(m) - 1)) basep = atomicAdd(&S->ncand, __popc(m));
+            basep = __shfl_sync(FULL, basep, __ffs(m) - 1);
+            if (ok) {
+              const int pos = basep + __popc(m & ((1u << lane) - 1u));
+              if (pos < CMAX) { c_bits[pos] = bits; c_id[pos] = id; }
             }
           }
         }
       }
-      const int nt0 = S->tcount;
-      for (int i0 = 0; i0 < nt0; i0 += THREADS) {
-        const int i = i0 + tid;
-        const bool ok = i < nt0;
-        const unsigned m = __ballot_sync(FULL, ok);
-        int basep = 0;
-        if (lane == (int)(__ffs(m) - 1)) basep = atomicAdd(&S->ncand, __popc(m));
-        basep = __shfl_sync(FULL, basep, __ffs(m) - 1);
-        if (ok) {
-          const int pos = basep + __popc(m & ((1u << lane) - 1u));
-          if (pos < CMAX) {
-            const int sl = t_list[i];
-            const int id = t_keys[sl];
-            const double v = par_score(((unsigned long long)t_acc[sl].y << 32) | t_acc[sl].x, init_mode, inv, mult,
-                                       (init_mode && id == self_id) ? base_self : 0.0);
-            c_bits[pos] = (unsigned long long)__double_as_longlong(v);
-            c_id[pos] = id;
+    };
+    // Lower bound of the cut from the previous basket (warm start): when the old basket is full, the new L-th largest
+    // score is almost always above half the old one. Candidates below theta are dropped while compacting, which is
+    // exact as long as at least L candidates remain (the L-th largest of a subset bounds the cut from below);
+    // otherwise theta is relaxed and the compaction repeated.
+    double theta0 = 0.0;
+    if (!init_mode && M.do_norm) {
+      const unsigned char* old = M.buf[write_slot ^ 1] + (size_t)p * slot_bytes(Lp);
+      const int* oid = reinterpret_cast<const int*>(old);
+      const double* osc = reinterpret_cast<const double*>(old + (size_t)Lp * 4);
+      unsigned long long mn = ~0ull;
+      long long cntv = 0;
+      for (int i = tid; i < Lp; i += THREADS)
+        if (oid[i] >= 0) { const unsigned long long b = (unsigned long long)__double_as_longlong(osc[score_index(i, Lp)]); mn = b < mn ? b : mn; cntv++; }
+      mn = block_reduce_min_ull(mn, S->red_a);
+      cntv = block_reduce_sum_ll(cntv, S->red_a);
+      if (cntv >= L) theta0 = __longlong_as_double((long long)mn);
+    }
+    // compaction with the warm-start filter; returns the candidate count (S->ncand), positions start at S->ncand = 0
+    auto compact_filtered = [&](bool from_dense, bool from_tail) -> int {
+      double th = theta0 * 0.5;
+      for (int attempt = 0;; attempt++) {
+        dropped_local = false;
+        __syncthreads();
+        if (tid == 0) S->ncand = 0;
+        __syncthreads();
+        compact(from_dense, from_tail, 0, (unsigned long long)__double_as_longlong(th));
+        __syncthreads();
+        const int c = S->ncand;
+        if (c >= L || th == 0.0) return c;
+        th = attempt == 0 ? th * 0.125 : 0.0;
+      }
+    };
+    // a node expected to outgrow the shared-memory structures binds its global table up front
+    // per-node memory of the previous update (M.ncand[p]): NEEDS_GLOBAL = outgrew shared memory -> bind a global table
+    // up front. The two-pass scheme pays when the dense range covers a small part of the label space (P.use_sketch, set
+    // by the host for graphs with more than 16 H nodes); small graphs stay single-pass.
+    constexpr int NEEDS_GLOBAL = 0x3fffffff;
+    const int hint = M.ncand[p];
+    const bool two_pass = R > 0 && P.use_sketch && nchunks == 1 && !init_mode && hint != NEEDS_GLOBAL;
+    if (!two_pass && S->table < 0 && hint == NEEDS_GLOBAL) bind_table();
+    PROF_MARK(1);
+    int n = 0;
+    if (two_pass) {
+      // The old basket is the best predictor of the new one: the buckets of its tail labels are marked up front and
+      // everything that falls into them is accumulated exactly during pass 1 already, so that tau (below) is the L-th
+      // largest of (dense labels + old-basket labels) -- close to the final cut -- and pass 2 only has to pick up the
+      // few new entrants.
+      for (int i = tid; i < R; i += THREADS) s_sk[i] = make_uint2(0u, 0u);
+      for (int i = tid; i < R / 32; i += THREADS) s_pre[i] = 0u;
+      __syncthreads();
+      {
+        const int* old_ids = reinterpret_cast<const int*>(M.buf[write_slot ^ 1] + (size_t)p * slot_bytes(Lp));
+        for (int i = tid; i < Lp; i += THREADS) {
+          const int k = old_ids[i];
+          if (k >= H) { const unsigned int b = hash_key(k) & (unsigned)(R > 0 ? R - 1 : 0); atomicOr(&s_pre[b >> 5], 1u << (b & 31)); }
+        }
+      }
+      __syncthreads();
+      const int tail_seen = __syncthreads_or(accumulate(1, false) ? 1 : 0);
+      const int nt_pre = S->tcount;
+      if (!S->spilled) n = compact_filtered(true, true);
+      __syncthreads();
+      if (n > CMAX) {
+        if (tid == 0) S->spilled = 1;
+      } else if (tail_seen && !S->spilled) {
+        // tau = L-th largest exact score so far (0 when there are not more than L candidates)
+        unsigned long long tau = 0ull;
+        if (n > L) {
+          bool tie;
+          int krem;
+          auto keyfn = [&](int i) { return c_bits[i]; };
+          auto all_ = [](int) { return true; };
+          tau = block_radix_select(n, L, keyfn, all_, S, &tie, &krem);
+        }
+        for (int i = tid; i < R / 32; i += THREADS) s_alive[i] = 0u;
+        __syncthreads();
+        int any_alive = 0;
+        for (int i = tid; i < R; i += THREADS) {
+          const uint2 a = s_sk[i];
+          if ((a.x | a.y) == 0u && tau != 0ull) continue;
+          if ((s_pre[i >> 5] >> (i & 31)) & 1u) continue;  // already exact
+          const unsigned long long bits =
+              (unsigned long long)__double_as_longlong(par_score(((unsigned long long)a.y << 32) | a.x, false, inv, mult, 0.0));
+          if (tau == 0ull || bits >= tau) { atomicOr(&s_alive[i >> 5], 1u << (i & 31)); any_alive = 1; }
+        }
+        any_alive = __syncthreads_or(any_alive);
+        if (any_alive) {
+          accumulate(2, false);
+          __syncthreads();
+          if (!S->spilled) {
+            compact(false, true, nt_pre, tau);
+            __syncthreads();
+            n = S->ncand;
+            if (n > CMAX && tid == 0) S->spilled = 1;
           }
         }
       }
       __syncthreads();
-      n = S->ncand;
-      if (n > CMAX && tid == 0) S->spilled = 1;  // more candidates than the compact arrays hold: take the global path
+    } else {
+      accumulate(0, S->table >= 0);
       __syncthreads();
+      // single-chunk node that stayed in shared memory: compact the candidates (score bits, label)
+      if (S->table < 0 && !S->spilled) {
+        n = compact_filtered(true, true);
+        if (n > CMAX && tid == 0) S->spilled = 1;  // more candidates than the compact arrays hold: take the global path
+        __syncthreads();
+      }
     }
+    PROF_MARK(2);
     if (S->spilled) {
-      // mispredicted: drop the partial sums, bind a table and run the chunk again with spilling enabled
+      // outgrew shared memory: drop the partial sums, bind a global table and run the item again in a single pass
       reset_shared();
       bind_table();
       put_self();
       __syncthreads();
-      accumulate(true);
+      accumulate(0, true);
       __syncthreads();
       PROF_MARK(3);
     }
@@ -617,7 +766,6 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
     }
 
     if (finalize) {
-      const double base_self = init_mode ? M.self_grank : 0.0;
       // candidates: compact arrays (score bits, label) -- in shared memory, or gathered once from the global table
       const unsigned long long* kb = c_bits;
       const int* ki = c_id;
@@ -655,6 +803,8 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
           s_ties += (tid == 0);
         }
         s_truncs += (tid == 0);
+      } else if (n == L && !use_global) {
+        if (__syncthreads_or(dropped_local ? 1 : 0)) s_truncs += (tid == 0);  // the filter already cut the rest away
       }
       auto selected = [&](unsigned long long bits, int label) -> bool {
         return bits > th.bits || (bits == th.bits && (th.id_max == 0x7fffffff || dense_of[label] <= th.id_max));
@@ -736,15 +886,11 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
           atomicExch(&P.tbl_inuse[S->table], 0u);
         }
       } else {
-        // clear the touched dense words through the compact list
-        for (int i = tid; i < n; i += THREADS) {
-          const int id = c_id[i];
-          if ((unsigned)id < (unsigned)H) s_dense[id] = make_uint2(0u, 0u);
-        }
+        for (int i = tid; i < H; i += THREADS) s_dense[i] = make_uint2(0u, 0u);
         for (int i = tid; i < H / 32; i += THREADS) s_zbits[i] = 0u;
       }
       if (tid == 0) {
-        M.ncand[p] = n;
+        M.ncand[p] = (use_global && !init_mode) ? NEEDS_GLOBAL : 0;  // a node that needed its global table binds it up front next time
         s_cands += (unsigned long long)n;
         s_nodes += 1;
         s_bytes += 12ull * (unsigned long long)old_cnt + 12ull * (unsigned long long)kept + 4ull + 16ull;

@@ -189,7 +189,7 @@ struct pprb200_session {
   // order-free class (out-degree > hub_threshold): work items [colour][0 = mid (128-thread CTAs), 1 = big (512)]
   int item_begin[2][2] = {{0, 0}, {0, 0}}, item_end[2][2] = {{0, 0}, {0, 0}};
   int n_items = 0;
-  int chunk = 1024, mid_deg = 64;
+  int chunk = 4096, mid_deg = 64;
   int* d_item_pos = nullptr;
   long long* d_item_off = nullptr;
   int* d_item_len = nullptr;
@@ -393,7 +393,8 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
 
   // storage order: colour-major; inside a colour the exact-order class first, then the order-free class
   // (mid, big); every class by out-degree descending (ties by dense id) -- big nodes first for load balance
-  if (const char* e = getenv("PPRB200_CHUNK")) s->chunk = std::min(PAR_CHUNK_MAX, std::max(32, atoi(e)));
+  s->chunk = n > 16 * 8192 ? 4096 : 1024;  // small graphs: finer items for load balance across the SMs
+  if (const char* e = getenv("PPRB200_CHUNK")) s->chunk = std::min(1 << 20, std::max(32, atoi(e)));
   s->mid_deg = default_mid_deg();
   std::vector<int32_t> order;
   int cls_begin[2][3], cls_end[2][3];
@@ -647,16 +648,16 @@ static int enqueue_cascade(pprb200_session* s, MergeParams P, int range_begin, i
   return PPRB200_OK;
 }
 
-template <int H, int TCAP, int CMAX, int COLCAP, int THREADS>
+template <int H, int TCAP, int CMAX, int COLCAP, int R, int THREADS>
 static cudaError_t launch_par(pprb200_session* s, const ParParams& P, int grid) {
-  const size_t smem = par_smem_bytes<H, TCAP, CMAX, COLCAP>() + 8 + par_queue_bytes(THREADS);
+  const size_t smem = par_smem_bytes<H, TCAP, CMAX, COLCAP, R>() + 8 + par_queue_bytes(THREADS);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(merge_par_kernel<H, TCAP, CMAX, COLCAP, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(merge_par_kernel<H, TCAP, CMAX, COLCAP, R, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  merge_par_kernel<H, TCAP, CMAX, COLCAP, THREADS><<<grid, THREADS, smem, s->stream>>>(P);
+  merge_par_kernel<H, TCAP, CMAX, COLCAP, R, THREADS><<<grid, THREADS, smem, s->stream>>>(P);
   s->launch_count++;
   return cudaGetLastError();
 }
@@ -674,6 +675,7 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
   P.node_tbl = s->d_node_tbl;
   P.node_done = s->d_node_done;
   P.n_ids = s->n;
+  P.use_sketch = s->n > 16 * 8192 ? 1 : 0;
   for (int cls = 1; cls >= 0; cls--) {
     const int b = s->item_begin[c][cls], e = s->item_end[c][cls];
     if (e == b) continue;
@@ -689,8 +691,8 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
     P.tbl_inuse = s->d_tbl_inuse + s->tbl_first[cls];
     P.tbl_count = s->d_tbl_count + s->tbl_first[cls];
     P.prof = s->d_prof ? s->d_prof + (size_t)cls * s->sm_count * 8 * 8 : nullptr;
-    cudaError_t err = cls == 1 ? launch_par<8192, 4096, 6144, PAR_CHUNK_MAX, 512>(s, P, std::min(s->sm_count, e - b))
-                               : launch_par<2048, 2048, 2048, PAR_MID_MAX, 128>(s, P, std::min(s->sm_count * 3, e - b));
+    cudaError_t err = cls == 1 ? launch_par<8192, 2048, 4096, PAR_CHUNK_MAX, 8192, 512>(s, P, std::min(s->sm_count, e - b))
+                               : launch_par<2048, 2048, 2048, PAR_MID_MAX, 0, 128>(s, P, std::min(s->sm_count * 3, e - b));
     if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_par launch failed: %s", cudaGetErrorString(err));
   }
   return PPRB200_OK;
