@@ -41,7 +41,7 @@ struct WalkParams {
   int queue_in_idx;           // -1: the range [src_begin, src_end)
   unsigned int* queue_out;    // nullable (fallback launch never overflows)
   int queue_out_idx;
-  unsigned long long* ws;     // fallback: gridDim.x tables of tcap 64-bit slots
+  unsigned long long* ws;     // fallback: gridDim.x x (table of tcap 64-bit slots + first-touch list of tcap 32-bit slot indices)
   PeerDev peers;              // multi-GPU: source index i of this rank maps to position src_begin + i*world + rank
 };
 
@@ -81,8 +81,16 @@ __global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   RunState* st = P.st;
   WalkShared* S = reinterpret_cast<WalkShared*>(smem);
-  WalkSlot* tbl = GLOBAL ? reinterpret_cast<WalkSlot*>(P.ws + (size_t)blockIdx.x * P.tcap)
+  // fallback tables are large (sized for the worst case) and sparsely used: their occupied slots are tracked in a list so
+  // that clearing and selecting cost O(distinct visited), not O(capacity)
+  unsigned char* gbase = GLOBAL ? reinterpret_cast<unsigned char*>(P.ws) + (size_t)blockIdx.x * P.tcap * (sizeof(WalkSlot) + sizeof(unsigned int)) : nullptr;
+  WalkSlot* tbl = GLOBAL ? reinterpret_cast<WalkSlot*>(gbase)
                          : reinterpret_cast<WalkSlot*>(smem + ((sizeof(WalkShared) + 15) & ~(size_t)15));
+  unsigned int* glist = GLOBAL ? reinterpret_cast<unsigned int*>(gbase + (size_t)P.tcap * sizeof(WalkSlot)) : nullptr;
+  if (GLOBAL) {
+    for (unsigned int i = threadIdx.x; i < P.tcap; i += THREADS) { tbl[i].key = WALK_EMPTY; tbl[i].count = 0u; }
+    __syncthreads();
+  }
   const int tid = threadIdx.x;
   const unsigned int mask = P.tcap - 1u;
   const int Lp = P.Lp, L = P.L;
@@ -108,13 +116,15 @@ __global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
     const uint32_t src_dense = (uint32_t)P.g.dense_of[self_label];
     const uint32_t self_word = (uint32_t)p | ((uint32_t)P.colour[src_dense] << COL_COLOUR_SHIFT);
 
-    for (unsigned int i = tid; i < P.tcap; i += THREADS) { tbl[i].key = WALK_EMPTY; tbl[i].count = 0u; }
+    if (!GLOBAL)
+      for (unsigned int i = tid; i < P.tcap; i += THREADS) { tbl[i].key = WALK_EMPTY; tbl[i].count = 0u; }
     if (tid == 0) { S->next_walk = 0u; S->ndistinct = 1u; S->overflow = 0; }
     __syncthreads();
     if (tid == 0) {  // res[src] = R (mccompletepathv2.h:124)
       const unsigned int h = hash_word(self_word) & mask;
       tbl[h].key = self_word;
       tbl[h].count = P.R;
+      if (GLOBAL) glist[0] = h;
     }
     __syncthreads();
 
@@ -141,7 +151,9 @@ __global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
           if (cur == WALK_EMPTY) {
             const uint32_t old = atomicCAS(&tbl[h].key, WALK_EMPTY, word);
             if (old == WALK_EMPTY) {
-              if (atomicAdd(&S->ndistinct, 1u) + 1u > P.limit) S->overflow = 1;
+              const unsigned int pos = atomicAdd(&S->ndistinct, 1u);
+              if (GLOBAL) glist[pos] = h;
+              if (pos + 1u > P.limit) S->overflow = 1;
               break;
             }
             if (old == word) break;
@@ -169,6 +181,8 @@ __global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
 
     // ---- top-L on (count desc, dense id asc), scores = count / R (:159-160) ----
     const int n = (int)S->ndistinct;
+    const int nscan = GLOBAL ? n : (int)P.tcap;                                 // candidates are scanned through the list / the table
+    auto slot_at = [&](int i) -> unsigned int { return GLOBAL ? glist[i] : (unsigned int)i; };
     auto word_label = [&](uint32_t wd) -> int { return (wd & COL_SINK) ? (int)(wd & ~COL_SINK) : P.g.label[wd & COL_POS_MASK]; };
     Threshold th;
     th.bits = 0ull;
@@ -178,16 +192,16 @@ __global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
       kept = L;
       bool tie;
       int krem;
-      auto occupied = [&](int i) { return tbl[i].key != WALK_EMPTY; };
-      auto keyfn = [&](int i) { return (unsigned long long)tbl[i].count; };
-      th.bits = block_radix_select((int)P.tcap, L, keyfn, occupied, &S->P, &tie, &krem);
+      auto occupied = [&](int i) { return tbl[slot_at(i)].key != WALK_EMPTY; };
+      auto keyfn = [&](int i) { return (unsigned long long)tbl[slot_at(i)].count; };
+      th.bits = block_radix_select(nscan, L, keyfn, occupied, &S->P, &tie, &krem);
       if (tie) {
         const unsigned long long tb = th.bits;
-        auto idkey = [&](int i) { return (unsigned long long)(0x7fffffff - P.g.dense_of[word_label(tbl[i].key)]); };
-        auto tied = [&](int i) { return tbl[i].key != WALK_EMPTY && (unsigned long long)tbl[i].count == tb; };
+        auto idkey = [&](int i) { return (unsigned long long)(0x7fffffff - P.g.dense_of[word_label(tbl[slot_at(i)].key)]); };
+        auto tied = [&](int i) { const WalkSlot t = tbl[slot_at(i)]; return t.key != WALK_EMPTY && (unsigned long long)t.count == tb; };
         bool tie2;
         int krem2;
-        const unsigned long long tid_key = block_radix_select((int)P.tcap, krem, idkey, tied, &S->P, &tie2, &krem2);
+        const unsigned long long tid_key = block_radix_select(nscan, krem, idkey, tied, &S->P, &tie2, &krem2);
         th.id_max = 0x7fffffff - (int)tid_key;
         tot_ties += (tid == 0);
       }
@@ -198,10 +212,11 @@ __global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
     double* out_sc = reinterpret_cast<double*>(out + (size_t)Lp * 4);
     if (tid == 0) S->P.out_pos = 0;
     __syncthreads();
-    for (unsigned int i = tid; i < P.tcap; i += THREADS) {
-      const uint32_t wd = tbl[i].key;
+    for (int i = tid; i < nscan; i += THREADS) {
+      const WalkSlot ts = tbl[slot_at(i)];
+      const uint32_t wd = ts.key;
       if (wd == WALK_EMPTY) continue;
-      const unsigned long long cnt = tbl[i].count;
+      const unsigned long long cnt = ts.count;
       bool sel = cnt > th.bits;
       int label = -1;
       if (!sel && cnt == th.bits) {
@@ -217,6 +232,8 @@ __global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
     }
     for (int i = kept + tid; i < Lp; i += THREADS) out_ids[i] = KEY_EMPTY;
     __syncthreads();
+    if (GLOBAL)  // leave the table empty for the next source
+      for (int i = tid; i < n; i += THREADS) { const unsigned int h = glist[i]; tbl[h].key = WALK_EMPTY; tbl[h].count = 0u; }
     publish_slot(P.peers, write_slot, (size_t)p * slot_bytes(Lp), slot_bytes(Lp), tid, THREADS);
     steps = (unsigned long long)block_reduce_sum_ll((long long)steps, S->P.red_a);
     if (tid == 0) {

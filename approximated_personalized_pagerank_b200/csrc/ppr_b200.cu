@@ -810,17 +810,24 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
 
 
 // ---- MCCompletePathV2 (mccompletepathv2.h:182-258, north-star semantics) ---------------------------------------
-template <bool GLOBAL>
-static cudaError_t launch_walk(pprb200_session* s, const WalkParams& P, int grid, size_t smem) {
+template <bool GLOBAL, int THREADS>
+static cudaError_t launch_walk_t(pprb200_session* s, const WalkParams& P, int grid, size_t smem) {
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(mc_walk_kernel<GLOBAL, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mc_walk_kernel<GLOBAL, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  mc_walk_kernel<GLOBAL, 256><<<grid, 256, smem, s->stream>>>(P);
+  mc_walk_kernel<GLOBAL, THREADS><<<grid, THREADS, smem, s->stream>>>(P);
   s->launch_count++;
   return cudaGetLastError();
+}
+
+// threads per source: a walk is sequential, so a CTA is busy for at least its longest walk (~ln(W)/(1-d) hops); with
+// fewer threads per source the average thread works about as long as that and little of the CTA idles in the tail
+template <bool GLOBAL>
+static cudaError_t launch_walk(pprb200_session* s, const WalkParams& P, int grid, size_t smem, int threads) {
+  return threads == 128 ? launch_walk_t<GLOBAL, 128>(s, P, grid, smem) : launch_walk_t<GLOBAL, 256>(s, P, grid, smem);
 }
 
 static uint32_t mc_coin_threshold(double damping) {
@@ -869,6 +876,8 @@ static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t 
     const double expect = std::min<double>((double)s->n + 1.0, 1.0 + (double)W * len * 0.8);
     unsigned int tcap = 1024;
     while ((double)tcap * 0.75 < expect && tcap < 16384u) tcap <<= 1;
+    int walk_threads = 256;  // measured on R-MAT-20, R=1000: 256 threads 19.8 G hops/s, 128 threads 12.3 G hops/s (fewer walks in flight)
+    if (const char* e = getenv("PPRB200_WALK_THREADS")) walk_threads = atoi(e) == 256 ? 256 : 128;
     if (const char* e = getenv("PPRB200_WALK_TCAP")) {  // test hook: force the fallback path
       unsigned int want = (unsigned int)std::max(1024, atoi(e));
       tcap = 1024;
@@ -877,27 +886,27 @@ static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t 
     P.tcap = tcap; P.limit = tcap * 3 / 4 - 1;
     P.work_idx = 0; P.queue_in = nullptr; P.queue_in_idx = -1; P.queue_out = s->d_queue[0]; P.queue_out_idx = 0;
     const size_t smem = ((sizeof(WalkShared) + 15) & ~(size_t)15) + (size_t)tcap * sizeof(WalkSlot);
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (smem + 1024)));
-    cudaError_t e = launch_walk<false>(s, P, std::max(1, std::min(s->M, s->sm_count * per_sm)), smem);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(walk_threads == 128 ? 16 : 8, (size_t)(227 * 1024) / (smem + 1024)));
+    cudaError_t e = launch_walk<false>(s, P, std::max(1, std::min(s->M, s->sm_count * per_sm)), smem, walk_threads);
     if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "mc_walk launch failed: %s", cudaGetErrorString(e));
     // fallback: sources that visited more distinct nodes than the shared table admits
     const unsigned long long worst = std::min<unsigned long long>((unsigned long long)s->n + 1ull, W * (unsigned long long)MC_MAX_STEPS + 1ull);
     if (worst > P.limit) {
       unsigned long long cap = 2048;
       while (cap < 2 * worst) cap <<= 1;
-      const size_t per = (size_t)cap * sizeof(WalkSlot);
+      const size_t per = (size_t)cap * (sizeof(WalkSlot) + sizeof(unsigned int));  // table + first-touch list
       const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)s->sm_count, ((size_t)2 << 30) / per));
       if ((size_t)grid * per > s->walk_ws_bytes) {
         dev_free(s->d_walk_ws);
         s->d_walk_ws = nullptr; s->walk_ws_bytes = 0;
-        if ((rc = dev_alloc(&s->d_walk_ws, (size_t)grid * cap))) return rc;
+        if ((rc = dev_alloc(&s->d_walk_ws, (size_t)grid * per / sizeof(unsigned long long) + 1))) return rc;
         s->walk_ws_bytes = (size_t)grid * per;
       }
       WalkParams Q = P;
       Q.tcap = (unsigned int)cap; Q.limit = 0xffffffffu;
       Q.work_idx = 1; Q.queue_in = s->d_queue[0]; Q.queue_in_idx = 0; Q.queue_out = nullptr; Q.queue_out_idx = 0;
       Q.ws = s->d_walk_ws;
-      e = launch_walk<true>(s, Q, grid, (sizeof(WalkShared) + 15) & ~(size_t)15);
+      e = launch_walk<true>(s, Q, grid, (sizeof(WalkShared) + 15) & ~(size_t)15, walk_threads);
       if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "mc_walk fallback launch failed: %s", cudaGetErrorString(e));
     }
     phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 1, 0, s->peers, 1);
