@@ -170,9 +170,12 @@ __device__ __forceinline__ int warp_sum_int(int v) {
 // are selected too (selected <=> key >= t); if tie, `krem` of the keys == t must still be chosen.
 // hist: 256 uint32 of shared memory private to the warp.
 // ------------------------------------------------------------------------------------------------
+// From the third pass on the keys still in play are probed first (min/max): a run of equal keys across the cut -- a
+// quarter of all truncations on power-law graphs -- ends the search at once instead of walking the remaining digits,
+// and keys that share more leading bits than one digit skip those positions. *ntied = keys equal to the threshold.
 template <typename KeyFn, typename PredFn>
 __device__ unsigned long long warp_radix_select(int n, int k, KeyFn key, PredFn pred, unsigned int* hist,
-                                                bool* tie, int* krem) {
+                                                bool* tie, int* krem, int* ntied = nullptr) {
   const int lane = lane_id();
   unsigned long long lo = ~0ull, hi = 0ull;
   for (int i = lane; i < n; i += 32)
@@ -185,14 +188,30 @@ __device__ unsigned long long warp_radix_select(int n, int k, KeyFn key, PredFn 
     int cnt = 0;
     for (int i = lane; i < n; i += 32) cnt += pred(i) ? 1 : 0;
     cnt = warp_sum_int(cnt);
-    if (cnt > k) { *tie = true; *krem = k; }
+    if (cnt > k) { *tie = true; *krem = k; if (ntied) *ntied = cnt; }
     return lo;
   }
   const int top = 63 - __clzll((long long)(lo ^ hi));
   unsigned long long known = (top == 63) ? 0ull : ~((2ull << top) - 1ull);
   unsigned long long prefix = hi & known;
   int shift = top - 7 > 0 ? top - 7 : 0;
-  for (;;) {
+  int in_bucket = 0;
+  for (int pass = 0;; pass++) {
+    if (pass >= 2) {
+      unsigned long long l2 = ~0ull, h2 = 0ull;
+      for (int i = lane; i < n; i += 32)
+        if (pred(i)) {
+          const unsigned long long b = key(i);
+          if ((b & known) == prefix) { l2 = b < l2 ? b : l2; h2 = b > h2 ? b : h2; }
+        }
+      l2 = warp_min_ull(l2);
+      h2 = warp_max_ull(h2);
+      if (l2 == h2) { *tie = true; *krem = k; if (ntied) *ntied = in_bucket; return l2; }
+      const int t2 = 63 - __clzll((long long)(l2 ^ h2));
+      known = ~((2ull << t2) - 1ull);
+      prefix = h2 & known;
+      shift = t2 - 7 > 0 ? t2 - 7 : 0;
+    }
     for (int i = lane; i < 256; i += 32) hist[i] = 0;
     __syncwarp();
     for (int i = lane; i < n; i += 32)
@@ -235,7 +254,8 @@ __device__ unsigned long long warp_radix_select(int n, int k, KeyFn key, PredFn 
     known |= 0xffull << shift;
     __syncwarp();
     if ((int)cnt_d == k) return prefix;  // whole bucket selected; unknown low bits of the threshold are 0
-    if (shift == 0) { *tie = true; *krem = k; return prefix; }
+    in_bucket = (int)cnt_d;
+    if (shift == 0) { *tie = true; *krem = k; if (ntied) *ntied = in_bucket; return prefix; }
     shift = shift - 8 > 0 ? shift - 8 : 0;
   }
 }

@@ -90,9 +90,10 @@ __device__ __forceinline__ long long block_reduce_sum_ll(long long v, unsigned l
   return r;
 }
 
-// CTA-wide version of warp_radix_select (device_common.cuh); same contract.
+// CTA-wide version of warp_radix_select (device_common.cuh); same contract (incl. the min/max probe from pass 3 on).
 template <typename KeyFn, typename PredFn>
-__device__ unsigned long long block_radix_select(int n, int k, KeyFn key, PredFn pred, ParShared* S, bool* tie, int* krem) {
+__device__ unsigned long long block_radix_select(int n, int k, KeyFn key, PredFn pred, ParShared* S, bool* tie, int* krem,
+                                                 int* ntied = nullptr) {
   const int tid = threadIdx.x, T = blockDim.x;
   unsigned long long lo = ~0ull, hi = 0ull;
   long long cnt = 0;
@@ -111,14 +112,34 @@ __device__ unsigned long long block_radix_select(int n, int k, KeyFn key, PredFn
   *krem = 0;
   if (lo == hi) {
     cnt = block_reduce_sum_ll(cnt, S->red_a);
-    if (cnt > k) { *tie = true; *krem = k; }
+    if (cnt > k) { *tie = true; *krem = k; if (ntied) *ntied = (int)cnt; }
     return lo;
   }
   const int top = 63 - __clzll((long long)(lo ^ hi));
   unsigned long long known = (top == 63) ? 0ull : ~((2ull << top) - 1ull);
   unsigned long long prefix = hi & known;
   int shift = top - 7 > 0 ? top - 7 : 0;
-  for (;;) {
+  int in_bucket = 0;
+  for (int pass = 0;; pass++) {
+    if (pass >= 2) {
+      unsigned long long l2 = ~0ull, h2 = 0ull;
+      for (int i0 = tid; i0 < n; i0 += 4 * T) {
+        unsigned long long b[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int i = i0 + u * T; ok[u] = i < n && pred(i); b[u] = ok[u] ? key(i) : 0ull; }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (ok[u] && (b[u] & known) == prefix) { l2 = b[u] < l2 ? b[u] : l2; h2 = b[u] > h2 ? b[u] : h2; }
+      }
+      l2 = block_reduce_min_ull(l2, S->red_a);
+      h2 = block_reduce_max_ull(h2, S->red_a);
+      if (l2 == h2) { *tie = true; *krem = k; if (ntied) *ntied = in_bucket; return l2; }
+      const int t2 = 63 - __clzll((long long)(l2 ^ h2));
+      known = ~((2ull << t2) - 1ull);
+      prefix = h2 & known;
+      shift = t2 - 7 > 0 ? t2 - 7 : 0;
+    }
     for (int i = tid; i < 256; i += T) S->hist[i] = 0;
     __syncthreads();
     for (int i0 = tid; i0 < n; i0 += 4 * T) {
@@ -160,9 +181,37 @@ __device__ unsigned long long block_radix_select(int n, int k, KeyFn key, PredFn
     known |= 0xffull << shift;
     __syncthreads();
     if (cnt_d == k) return prefix;
-    if (shift == 0) { *tie = true; *krem = k; return prefix; }
+    in_bucket = cnt_d;
+    if (shift == 0) { *tie = true; *krem = k; if (ntied) *ntied = in_bucket; return prefix; }
     shift = shift - 8 > 0 ? shift - 8 : 0;
   }
+}
+
+// Cut through a run of `ntied` (<= 32) candidates whose key equals `tb`: the `krem` smallest dense ids stay. The tied
+// elements are gathered into shared memory and ranked by warp 0 with shuffles -- one scan instead of a second radix
+// select with a dense_of lookup per pass. Returns id_max. All threads of the CTA must call it.
+template <typename KeyFn, typename PredFn, typename DenseFn>
+__device__ int block_small_tie_cut(int n, int krem, unsigned long long tb, KeyFn key, PredFn pred, DenseFn dense, ParShared* S) {
+  const int tid = threadIdx.x, T = blockDim.x;
+  __syncthreads();
+  if (tid == 0) S->sel_cnt = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += T)
+    if (pred(i) && key(i) == tb) { const int pos = atomicAdd(&S->sel_cnt, 1); if (pos < 32) S->hist[pos] = (unsigned int)dense(i); }
+  __syncthreads();
+  if (tid < 32) {
+    const int m = S->sel_cnt < 32 ? S->sel_cnt : 32;
+    const int myd = tid < m ? (int)S->hist[tid] : 0x7fffffff;
+    int rank = 0;
+    for (int j = 0; j < m; j++) rank += __shfl_sync(FULL, myd, j) < myd;
+    const unsigned who = __ballot_sync(FULL, tid < m && rank == krem - 1);
+    const int cut = __shfl_sync(FULL, myd, __ffs(who) - 1);
+    if (tid == 0) S->sel_digit = cut;
+  }
+  __syncthreads();
+  const int r = S->sel_digit;
+  __syncthreads();
+  return r;
 }
 
 // fixed-point word -> score. init mode: the word is a multiplicity m and the score is `base + mult + ... + mult`
@@ -791,15 +840,21 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
         bool tie;
         int krem;
         auto keyfn = [&](int i) { return kb[i]; };
-        th.bits = block_radix_select(n, L, keyfn, all, S, &tie, &krem);
+        int ntied = 0;
+        th.bits = block_radix_select(n, L, keyfn, all, S, &tie, &krem, &ntied);
         if (tie) {
           const unsigned long long tb = th.bits;
-          auto idkey = [&](int i) { return (unsigned long long)(0x7fffffff - dense_of[ki[i]]); };
-          auto tied = [&](int i) { return kb[i] == tb; };
-          bool tie2;
-          int krem2;
-          const unsigned long long tid_key = block_radix_select(n, krem, idkey, tied, S, &tie2, &krem2);
-          th.id_max = 0x7fffffff - (int)tid_key;
+          if (ntied <= 32) {
+            auto densefn = [&](int i) { return dense_of[ki[i]]; };
+            th.id_max = block_small_tie_cut(n, krem, tb, keyfn, all, densefn, S);
+          } else {
+            auto idkey = [&](int i) { return (unsigned long long)(0x7fffffff - dense_of[ki[i]]); };
+            auto tied = [&](int i) { return kb[i] == tb; };
+            bool tie2;
+            int krem2;
+            const unsigned long long tid_key = block_radix_select(n, krem, idkey, tied, S, &tie2, &krem2);
+            th.id_max = 0x7fffffff - (int)tid_key;
+          }
           s_ties += (tid == 0);
         }
         s_truncs += (tid == 0);

@@ -235,15 +235,36 @@ __device__ bool merge_node_seq(const MergeParams& P, const WarpTable<IdxT>& T, u
     int krem;
     auto keyfn = [&](int i) { return (unsigned long long)__double_as_longlong(T.vals[T.list[i]]); };
     auto all = [&](int) { return true; };
-    th.bits = warp_radix_select(n, L, keyfn, all, hist, &tie, &krem);
+    int ntied = 0;
+    th.bits = warp_radix_select(n, L, keyfn, all, hist, &tie, &krem, &ntied);
     if (tie) {
       const unsigned long long tb = th.bits;
-      auto idkey = [&](int i) { return (unsigned long long)(0x7fffffff - P.g.dense_of[T.keys[T.list[i]]]); };
-      auto tied = [&](int i) { return (unsigned long long)__double_as_longlong(T.vals[T.list[i]]) == tb; };
-      bool tie2;
-      int krem2;
-      const unsigned long long tid = warp_radix_select(n, krem, idkey, tied, hist, &tie2, &krem2);
-      th.id_max = 0x7fffffff - (int)tid;
+      if (ntied <= 32) {
+        // few tied candidates (the usual case): gather their dense ids and rank them with shuffles
+        int* sd = reinterpret_cast<int*>(hist);
+        int off = 0;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+          const int i = i0 + lane;
+          const bool in = i < n && (unsigned long long)__double_as_longlong(T.vals[T.list[i]]) == tb;
+          const unsigned m = __ballot_sync(FULL, in);
+          if (in) sd[off + __popc(m & ((1u << lane) - 1u))] = P.g.dense_of[T.keys[T.list[i]]];
+          off += __popc(m);
+        }
+        __syncwarp();
+        const int myd = lane < off ? sd[lane] : 0x7fffffff;
+        int rank = 0;
+        for (int j = 0; j < off; j++) rank += __shfl_sync(FULL, myd, j) < myd;
+        const unsigned who = __ballot_sync(FULL, lane < off && rank == krem - 1);
+        th.id_max = __shfl_sync(FULL, myd, __ffs(who) - 1);
+        __syncwarp();
+      } else {
+        auto idkey = [&](int i) { return (unsigned long long)(0x7fffffff - P.g.dense_of[T.keys[T.list[i]]]); };
+        auto tied = [&](int i) { return (unsigned long long)__double_as_longlong(T.vals[T.list[i]]) == tb; };
+        bool tie2;
+        int krem2;
+        const unsigned long long tid = warp_radix_select(n, krem, idkey, tied, hist, &tie2, &krem2);
+        th.id_max = 0x7fffffff - (int)tid;
+      }
       st_ties += (lane == 0);
     }
     st_truncs += (lane == 0);
