@@ -280,12 +280,13 @@ __device__ __forceinline__ void fixed_add_shared(uint2* word, unsigned long long
 }
 
 constexpr int PAR_CHUNK_MAX = 1024;  // column words of the big class are staged in shared memory in tiles of this many successors
+constexpr int PAR_PRE = 128;         // old-basket tail labels that get an exact accumulator of their own during pass 1
 constexpr int PAR_MID_MAX = 128;     // largest out-degree the mid class may be configured for
 
 template <int H, int TCAP, int CMAX, int COLCAP, int R>
 constexpr size_t par_smem_bytes() {
-  return (size_t)H * 8 + (size_t)TCAP * 14 + (size_t)H / 8 + (size_t)CMAX * 12 + (size_t)COLCAP * 4 + (size_t)R * 8 + (size_t)R / 4 +
-         sizeof(ParShared);
+  return (size_t)H * 8 + (size_t)TCAP * 14 + (size_t)H / 8 + (size_t)CMAX * 12 + (size_t)COLCAP * 4 +
+         (R > 0 ? (size_t)R * 8 + (size_t)R / 8 + (size_t)R + (size_t)PAR_PRE * 16 : 0) + sizeof(ParShared);
 }
 constexpr size_t par_queue_bytes(int threads) { return (size_t)(threads / 32) * 64 * 12; }
 
@@ -329,7 +330,10 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
   uint32_t* s_col = reinterpret_cast<uint32_t*>(sp); sp += (size_t)COLCAP * 4;
   uint2* s_sk = reinterpret_cast<uint2*>(sp); sp += (size_t)R * 8;                     // sketch buckets (fixed point)
   unsigned int* s_alive = reinterpret_cast<unsigned int*>(sp); sp += (size_t)R / 8;    // buckets that may hold a top-L label
-  unsigned int* s_pre = reinterpret_cast<unsigned int*>(sp); sp += (size_t)R / 8;      // buckets of the old basket's tail labels
+  uint2* s_pacc = reinterpret_cast<uint2*>(sp); sp += (R > 0 ? (size_t)PAR_PRE * 8 : 0);   // exact sums of old-basket tail labels
+  int* s_pkey = reinterpret_cast<int*>(sp); sp += (R > 0 ? (size_t)PAR_PRE * 4 : 0);       //   their labels (-1: slot unused)
+  unsigned char* s_ptouch = sp; sp += (R > 0 ? (size_t)PAR_PRE * 4 : 0);                   //   touched flags (padded)
+  unsigned char* s_pslot = sp; sp += (size_t)R;                                            // bucket -> slot + 1 (0: none)
   unsigned int* s_zbits = reinterpret_cast<unsigned int*>(sp); sp += (size_t)H / 8;  // dense labels touched with a 0 word
   unsigned short* t_list = reinterpret_cast<unsigned short*>(sp); sp += (size_t)TCAP * 2;
   ParShared* S = reinterpret_cast<ParShared*>(sp); sp += (sizeof(ParShared) + 7) & ~(size_t)7;
@@ -345,6 +349,7 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
   for (int i = tid; i < H; i += THREADS) s_dense[i] = make_uint2(0u, 0u);
   for (int i = tid; i < H / 32; i += THREADS) s_zbits[i] = 0u;
   for (int i = tid; i < TCAP; i += THREADS) { t_keys[i] = KEY_EMPTY; t_acc[i] = make_uint2(0u, 0u); }
+  for (int i = tid; i < R; i += THREADS) s_pslot[i] = 0;
   if (tid == 0) { S->tcount = 0; S->spilled = 0; S->table = -1; }
   __syncthreads();
 
@@ -504,19 +509,13 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
           slow = false;
           if (k >= H) {
             const unsigned int b = hash_key(k) & (unsigned)(R > 0 ? R - 1 : 0);
-            slow = (s_alive[b >> 5] >> (b & 31)) & 1u;
+            const int ps = s_pslot[b];
+            slow = ((s_alive[b >> 5] >> (b & 31)) & 1u) && !(ps && s_pkey[ps - 1] == k);  // pre-slot labels are exact already
           }
         } else {
           const bool fast = dense && xf != 0ull;
           if (fast) fixed_add_shared(&s_dense[k], xf);
-          if (pass == 1 && k >= H) {
-            tail_seen = true;
-            const unsigned int b = hash_key(k) & (unsigned)(R > 0 ? R - 1 : 0);
-            if (xf) fixed_add_shared(&s_sk[b], xf);
-            slow = (s_pre[b >> 5] >> (b & 31)) & 1u;  // bucket of an old-basket label: accumulate exactly right away
-          } else {
-            slow = !fast && k >= 0;
-          }
+          slow = !fast && k >= 0;
         }
         const unsigned m = __ballot_sync(FULL, slow);
         if (m) {
@@ -559,7 +558,24 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
           const uint32_t c = s_col[j];
           if (c & COL_SINK) {
             const double x = (M.mode == MODE_GRANK) ? M.self_grank : 1.0;
-            contribute(lane == 0 ? (int)(c & ~COL_SINK) : -1, (unsigned long long)__double2ll_rn(x * fscale));
+            const int k = (int)(c & ~COL_SINK);
+            const unsigned long long xf = (unsigned long long)__double2ll_rn(x * fscale);
+            if (pass == 1) {
+              if (lane == 0) {
+                if (k < H) {
+                  if (xf) fixed_add_shared(&s_dense[k], xf);
+                  else atomicOr(&s_zbits[k >> 5], 1u << (k & 31));
+                } else {
+                  tail_seen = true;
+                  const unsigned int b = hash_key(k) & (unsigned)(R > 0 ? R - 1 : 0);
+                  const int ps = s_pslot[b];
+                  if (ps && s_pkey[ps - 1] == k) { if (xf) fixed_add_shared(&s_pacc[ps - 1], xf); s_ptouch[ps - 1] = 1; }
+                  else if (xf) fixed_add_shared(&s_sk[b], xf);
+                }
+              }
+            } else {
+              contribute(lane == 0 ? k : -1, xf);
+            }
             merged += (lane == 0);
           } else {
             for (int g0 = 0; g0 < groups; g0 += 32) {
@@ -572,10 +588,49 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
               }
               const int ids[4] = {fr.id.x, fr.id.y, fr.id.z, fr.id.w};
               const double xs[4] = {fr.sa.x, fr.sa.y, fr.sb.x, fr.sb.y};
+              if (pass == 1) {
+                // lean pass: no queue, no votes -- every entry is one or two shared-memory atomics on the dense word, on the
+                // exact accumulator of an old-basket label, or on its sketch bucket
 #pragma unroll
-              for (int e = 0; e < 4; e++) {
-                contribute(ids[e], (unsigned long long)__double2ll_rn(xs[e] * fscale));
-                merged += (ids[e] >= 0);
+                for (int e = 0; e < 4; e++) {
+                  const int k = ids[e];
+                  if (k < 0) continue;
+                  merged++;
+                  const unsigned long long xf = (unsigned long long)__double2ll_rn(xs[e] * fscale);
+                  if (k < H) {
+                    if (xf) fixed_add_shared(&s_dense[k], xf);
+                    else atomicOr(&s_zbits[k >> 5], 1u << (k & 31));
+                  } else {
+                    tail_seen = true;
+                    const unsigned int b = hash_key(k) & (unsigned)(R > 0 ? R - 1 : 0);
+                    const int ps = s_pslot[b];
+                    if (ps && s_pkey[ps - 1] == k) {
+                      if (xf) fixed_add_shared(&s_pacc[ps - 1], xf);
+                      s_ptouch[ps - 1] = 1;
+                    } else if (xf) {
+                      fixed_add_shared(&s_sk[b], xf);
+                    }
+                  }
+                }
+              } else if (pass == 2) {
+                // most baskets hold no surviving tail label: one vote skips them
+                bool mine = false;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                  const int k = ids[e];
+                  if (k >= H) { const unsigned int b = hash_key(k) & (unsigned)(R > 0 ? R - 1 : 0); mine |= (s_alive[b >> 5] >> (b & 31)) & 1u; }
+                  merged += (k >= 0);
+                }
+                if (__any_sync(FULL, mine)) {
+#pragma unroll
+                  for (int e = 0; e < 4; e++) contribute(ids[e], (unsigned long long)__double2ll_rn(xs[e] * fscale));
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                  contribute(ids[e], (unsigned long long)__double2ll_rn(xs[e] * fscale));
+                  merged += (ids[e] >= 0);
+                }
               }
             }
           }
@@ -603,7 +658,7 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
     // select the sources, positions continue from S->ncand
     const double base_self = init_mode ? M.self_grank : 0.0;
     bool dropped_local = false;  // this thread left a candidate out of the compact arrays (below the lower bound)
-    auto compact = [&](bool from_dense, bool from_tail, int tail_from, unsigned long long theta) {
+    auto compact = [&](bool from_dense, bool from_tail, int tail_from, unsigned long long theta, bool from_pre = false) {
       if (from_dense)
         for (int i0 = 0; i0 < H; i0 += THREADS) {
           const int i = i0 + tid;
@@ -627,6 +682,25 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
             }
           }
         }
+      if (from_pre && tid < 32 * ((PAR_PRE + 31) / 32)) {  // the first PAR_PRE/32 warps, whole warps
+        bool ok = tid < PAR_PRE && s_pkey[tid] >= 0 && s_ptouch[tid];
+        unsigned long long bits = 0ull;
+        if (ok) {
+          bits = (unsigned long long)__double_as_longlong(par_score(((unsigned long long)s_pacc[tid].y << 32) | s_pacc[tid].x, false, inv, mult, 0.0));
+          ok = bits >= theta;
+          dropped_local |= !ok;
+        }
+        const unsigned m = __ballot_sync(FULL, ok);
+        if (m) {
+          int basep = 0;
+          if (lane == (int)(__ffs(m) - 1)) basep = atomicAdd(&S->ncand, __popc(m));
+          basep = __shfl_sync(FULL, basep, __ffs(m) - 1);
+          if (ok) {
+            const int pos = basep + __popc(m & ((1u << lane) - 1u));
+            if (pos < CMAX) { c_bits[pos] = bits; c_id[pos] = s_pkey[tid]; }
+          }
+        }
+      }
       if (from_tail) {
         const int nt0 = S->tcount;
         for (int i0 = tail_from; i0 < nt0; i0 += THREADS) {
@@ -673,14 +747,14 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
       if (cntv >= L) theta0 = __longlong_as_double((long long)mn);
     }
     // compaction with the warm-start filter; returns the candidate count (S->ncand), positions start at S->ncand = 0
-    auto compact_filtered = [&](bool from_dense, bool from_tail) -> int {
+    auto compact_filtered = [&](bool from_dense, bool from_tail, bool from_pre = false) -> int {
       double th = theta0 * 0.5;
       for (int attempt = 0;; attempt++) {
         dropped_local = false;
         __syncthreads();
         if (tid == 0) S->ncand = 0;
         __syncthreads();
-        compact(from_dense, from_tail, 0, (unsigned long long)__double_as_longlong(th));
+        compact(from_dense, from_tail, 0, (unsigned long long)__double_as_longlong(th), from_pre);
         __syncthreads();
         const int c = S->ncand;
         if (c >= L || th == 0.0) return c;
@@ -689,67 +763,82 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
     };
     // a node expected to outgrow the shared-memory structures binds its global table up front
     // per-node memory of the previous update (M.ncand[p]): NEEDS_GLOBAL = outgrew shared memory -> bind a global table
-    // up front. The two-pass scheme pays when the dense range covers a small part of the label space (P.use_sketch, set
-    // by the host for graphs with more than 16 H nodes); small graphs stay single-pass.
+    // up front. Single-item nodes of the big class take the two-pass scheme (P.use_sketch; measured faster than the
+    // single pass from R-MAT-16 to R-MAT-22, the more so the smaller the share of the label space the dense range covers).
     constexpr int NEEDS_GLOBAL = 0x3fffffff;
     const int hint = M.ncand[p];
     const bool two_pass = R > 0 && P.use_sketch && nchunks == 1 && !init_mode && hint != NEEDS_GLOBAL;
     if (!two_pass && S->table < 0 && hint == NEEDS_GLOBAL) bind_table();
     PROF_MARK(1);
     int n = 0;
+    int my_bucket = -1;  // sketch bucket whose exact pre-slot this thread owns (two-pass only)
     if (two_pass) {
-      // The old basket is the best predictor of the new one: the buckets of its tail labels are marked up front and
-      // everything that falls into them is accumulated exactly during pass 1 already, so that tau (below) is the L-th
-      // largest of (dense labels + old-basket labels) -- close to the final cut -- and pass 2 only has to pick up the
-      // few new entrants.
+      // The old basket is the best predictor of the new one: its tail labels get exact accumulators of their own for
+      // pass 1 (one per sketch bucket, first come first served), so that tau (below) is the L-th largest of (dense labels
+      // + old-basket labels) -- close to the final cut -- and pass 2 only has to pick up the few new entrants.
       for (int i = tid; i < R; i += THREADS) s_sk[i] = make_uint2(0u, 0u);
-      for (int i = tid; i < R / 32; i += THREADS) s_pre[i] = 0u;
-      __syncthreads();
-      {
+      if (tid < PAR_PRE) {
         const int* old_ids = reinterpret_cast<const int*>(M.buf[write_slot ^ 1] + (size_t)p * slot_bytes(Lp));
-        for (int i = tid; i < Lp; i += THREADS) {
-          const int k = old_ids[i];
-          if (k >= H) { const unsigned int b = hash_key(k) & (unsigned)(R > 0 ? R - 1 : 0); atomicOr(&s_pre[b >> 5], 1u << (b & 31)); }
+        const int k = tid < Lp ? old_ids[tid] : -1;
+        s_pkey[tid] = -1;
+        s_pacc[tid] = make_uint2(0u, 0u);
+        s_ptouch[tid] = 0;
+        // (the node's own label keeps its place in the tail table, where put_self started it; two old labels in one
+        // bucket: the last writer owns it, the other stays in the sketch)
+        if (k >= H && k != self_id) { my_bucket = (int)(hash_key(k) & (unsigned)(R > 0 ? R - 1 : 0)); s_pslot[my_bucket] = (unsigned char)(tid + 1); }
+      }
+      __syncthreads();
+      if (tid < PAR_PRE && my_bucket >= 0) {
+        if (s_pslot[my_bucket] == (unsigned char)(tid + 1)) {
+          const int* old_ids = reinterpret_cast<const int*>(M.buf[write_slot ^ 1] + (size_t)p * slot_bytes(Lp));
+          s_pkey[tid] = old_ids[tid];
+        } else {
+          my_bucket = -1;
         }
       }
       __syncthreads();
       const int tail_seen = __syncthreads_or(accumulate(1, false) ? 1 : 0);
-      const int nt_pre = S->tcount;
-      if (!S->spilled) n = compact_filtered(true, true);
+      n = compact_filtered(true, false, true);
       __syncthreads();
       if (n > CMAX) {
         if (tid == 0) S->spilled = 1;
-      } else if (tail_seen && !S->spilled) {
-        // tau = L-th largest exact score so far (0 when there are not more than L candidates)
+      } else {
         unsigned long long tau = 0ull;
-        if (n > L) {
-          bool tie;
-          int krem;
-          auto keyfn = [&](int i) { return c_bits[i]; };
-          auto all_ = [](int) { return true; };
-          tau = block_radix_select(n, L, keyfn, all_, S, &tie, &krem);
-        }
-        for (int i = tid; i < R / 32; i += THREADS) s_alive[i] = 0u;
-        __syncthreads();
-        int any_alive = 0;
-        for (int i = tid; i < R; i += THREADS) {
-          const uint2 a = s_sk[i];
-          if ((a.x | a.y) == 0u && tau != 0ull) continue;
-          if ((s_pre[i >> 5] >> (i & 31)) & 1u) continue;  // already exact
-          const unsigned long long bits =
-              (unsigned long long)__double_as_longlong(par_score(((unsigned long long)a.y << 32) | a.x, false, inv, mult, 0.0));
-          if (tau == 0ull || bits >= tau) { atomicOr(&s_alive[i >> 5], 1u << (i & 31)); any_alive = 1; }
-        }
-        any_alive = __syncthreads_or(any_alive);
-        if (any_alive) {
-          accumulate(2, false);
-          __syncthreads();
-          if (!S->spilled) {
-            compact(false, true, nt_pre, tau);
-            __syncthreads();
-            n = S->ncand;
-            if (n > CMAX && tid == 0) S->spilled = 1;
+        if (tail_seen) {
+          // tau = L-th largest exact score so far (0 when there are not more than L candidates)
+          if (n > L) {
+            bool tie;
+            int krem;
+            auto keyfn = [&](int i) { return c_bits[i]; };
+            auto all_ = [](int) { return true; };
+            tau = block_radix_select(n, L, keyfn, all_, S, &tie, &krem);
           }
+          for (int i = tid; i < R / 32; i += THREADS) s_alive[i] = 0u;
+          __syncthreads();
+          int any_alive = 0;
+          for (int i = tid; i < R; i += THREADS) {
+            const uint2 a = s_sk[i];
+            if ((a.x | a.y) == 0u && tau != 0ull) continue;
+            const unsigned long long bits =
+                (unsigned long long)__double_as_longlong(par_score(((unsigned long long)a.y << 32) | a.x, false, inv, mult, 0.0));
+            if (tau == 0ull || bits >= tau) { atomicOr(&s_alive[i >> 5], 1u << (i & 31)); any_alive = 1; }
+          }
+          if (tid == 0 && self_id >= H) {  // contributions to the node's own (tail) label went to the sketch: always exact in pass 2
+            const unsigned int b = hash_key(self_id) & (unsigned)(R > 0 ? R - 1 : 0);
+            atomicOr(&s_alive[b >> 5], 1u << (b & 31));
+            any_alive = 1;
+          }
+          any_alive = __syncthreads_or(any_alive);
+          if (any_alive) {
+            accumulate(2, false);
+            __syncthreads();
+          }
+        }
+        if (!S->spilled) {
+          compact(false, true, 0, tau);  // the tail table: the node itself (if a tail label) and the survivors, all exact now
+          __syncthreads();
+          n = S->ncand;
+          if (n > CMAX && tid == 0) S->spilled = 1;
         }
       }
       __syncthreads();
@@ -905,6 +994,11 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
                 const uint2 a = s_dense[ids[e]];
                 found = dense_touched(ids[e], a);
                 nv_ = par_score(((unsigned long long)a.y << 32) | a.x, false, inv, mult, 0.0);
+              } else if (R > 0 && two_pass && s_pslot[hash_key(ids[e]) & (unsigned)(R > 0 ? R - 1 : 0)] &&
+                         s_pkey[s_pslot[hash_key(ids[e]) & (unsigned)(R > 0 ? R - 1 : 0)] - 1] == ids[e]) {
+                const int ps = s_pslot[hash_key(ids[e]) & (unsigned)(R > 0 ? R - 1 : 0)] - 1;
+                found = s_ptouch[ps] != 0;
+                nv_ = par_score(((unsigned long long)s_pacc[ps].y << 32) | s_pacc[ps].x, false, inv, mult, 0.0);
               } else {
                 for (unsigned int h = hash_key(ids[e]) & (TCAP - 1);; h = (h + 1) & (TCAP - 1)) {
                   const int cur = t_keys[h];
@@ -952,6 +1046,7 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
       }
     }
     PROF_MARK(6);
+    if (R > 0 && my_bucket >= 0) s_pslot[my_bucket] = 0;  // leave the bucket map clean for the next node
     // ---- reset the tail table through its list ----
     for (int i = tid; i < nt; i += THREADS) {
       const int s = t_list[i];

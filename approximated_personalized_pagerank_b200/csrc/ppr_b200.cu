@@ -675,7 +675,8 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
   P.node_tbl = s->d_node_tbl;
   P.node_done = s->d_node_done;
   P.n_ids = s->n;
-  P.use_sketch = s->n > 16 * 8192 ? 1 : 0;
+  P.use_sketch = 1;  // two-pass merge for single-item nodes of the big class (PPRB200_SKETCH=0: single pass, for A/B runs)
+  if (const char* e = getenv("PPRB200_SKETCH")) P.use_sketch = atoi(e) != 0;
   for (int cls = 1; cls >= 0; cls--) {
     const int b = s->item_begin[c][cls], e = s->item_end[c][cls];
     if (e == b) continue;
@@ -691,7 +692,7 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
     P.tbl_inuse = s->d_tbl_inuse + s->tbl_first[cls];
     P.tbl_count = s->d_tbl_count + s->tbl_first[cls];
     P.prof = s->d_prof ? s->d_prof + (size_t)cls * s->sm_count * 8 * 8 : nullptr;
-    cudaError_t err = cls == 1 ? launch_par<8192, 2048, 4096, PAR_CHUNK_MAX, 8192, 512>(s, P, std::min(s->sm_count, e - b))
+    cudaError_t err = cls == 1 ? launch_par<8192, 2048, 3072, PAR_CHUNK_MAX, 8192, 512>(s, P, std::min(s->sm_count, e - b))
                                : launch_par<2048, 2048, 2048, PAR_MID_MAX, 0, 128>(s, P, std::min(s->sm_count * 3, e - b));
     if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_par launch failed: %s", cudaGetErrorString(err));
   }
