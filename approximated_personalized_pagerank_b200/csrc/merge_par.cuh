@@ -312,7 +312,7 @@ __device__ __forceinline__ void load_frag_all(const unsigned char* slot, int Lp,
 // buckets. Everything stays in shared memory; the result is the same set of sums the single pass produces for every
 // candidate that can be selected.
 template <int H, int TCAP, int CMAX, int COLCAP, int R, int THREADS>
-__global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
+__global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 3 : 1)) merge_par_kernel(ParParams P) {
   constexpr int TLIMIT = TCAP * 13 / 16 - THREADS;
   constexpr int NW = THREADS / 32;
   static_assert(H + TCAP <= 65536, "candidate references are 16 bit");
@@ -353,9 +353,7 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
   if (tid == 0) { S->tcount = 0; S->spilled = 0; S->table = -1; }
   __syncthreads();
 
-  int read_slot[2];
-  read_slot[0] = st->slot[0];
-  read_slot[1] = st->slot[1];
+  const int read_slot0 = st->slot[0], read_slot1 = st->slot[1];  // (two scalars: a dynamically indexed array would live in local memory)
 
   unsigned long long s_merged = 0, s_edges = 0, s_cands = 0, s_truncs = 0, s_ties = 0, s_bytes = 0, s_nodes = 0, s_requeue = 0;
 
@@ -477,7 +475,7 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
       bool tail_seen = false;
       // warp w merges successors w, w+NW, ... of a tile with the next two baskets already in flight
       auto slot_of = [&](uint32_t cc) -> const unsigned char* {
-        return M.buf[read_slot[(cc >> COL_COLOUR_SHIFT) & 1u]] + (size_t)(cc & COL_POS_MASK) * slot_bytes(Lp);
+        return M.buf[((cc >> COL_COLOUR_SHIFT) & 1u) ? read_slot1 : read_slot0] + (size_t)(cc & COL_POS_MASK) * slot_bytes(Lp);
       };
       // Entries that miss the fast paths (tail labels, zero products) are rare but slow (hash probe, CAS); taken
       // inline they would stall the whole warp behind two or three lanes. They are parked in a per-warp queue and
@@ -798,6 +796,7 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
       }
       __syncthreads();
       const int tail_seen = __syncthreads_or(accumulate(1, false) ? 1 : 0);
+      PROF_MARK(2);
       n = compact_filtered(true, false, true);
       __syncthreads();
       if (n > CMAX) {
@@ -829,6 +828,7 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
             any_alive = 1;
           }
           any_alive = __syncthreads_or(any_alive);
+          PROF_MARK(3);
           if (any_alive) {
             accumulate(2, false);
             __syncthreads();
@@ -842,6 +842,7 @@ __global__ void __launch_bounds__(THREADS) merge_par_kernel(ParParams P) {
         }
       }
       __syncthreads();
+      PROF_MARK(4);
     } else {
       accumulate(0, S->table >= 0);
       __syncthreads();

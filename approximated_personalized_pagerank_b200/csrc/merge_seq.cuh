@@ -100,7 +100,7 @@ __device__ __forceinline__ void load_frag(const unsigned char* slot, int Lp, int
 // Per-warp statistics are accumulated into the reference arguments.
 template <typename IdxT>
 __device__ bool merge_node_seq(const MergeParams& P, const WarpTable<IdxT>& T, unsigned int* hist, int* s_count,
-                               int p, int write_slot, const int* read_slot, unsigned long long& st_merged,
+                               int p, int write_slot, int read_slot0, int read_slot1, unsigned long long& st_merged,
                                unsigned long long& st_edges, unsigned long long& st_cands,
                                unsigned long long& st_truncs, unsigned long long& st_ties,
                                unsigned long long& st_bytes, long long& warp_maxdiff) {
@@ -171,7 +171,7 @@ __device__ bool merge_node_seq(const MergeParams& P, const WarpTable<IdxT>& T, u
       fr->sa = fr->sb = make_double2(0.0, 0.0);
       const uint32_t c = __shfl_sync(FULL, mycol, j < chunk ? j : 0);
       if (j < chunk && !(c & COL_SINK) && lane < groups) {
-        const unsigned char* slot = P.buf[read_slot[(c >> COL_COLOUR_SHIFT) & 1u]] + (size_t)(c & COL_POS_MASK) * slot_bytes(Lp);
+        const unsigned char* slot = P.buf[((c >> COL_COLOUR_SHIFT) & 1u) ? read_slot1 : read_slot0] + (size_t)(c & COL_POS_MASK) * slot_bytes(Lp);
         const int4* ids = reinterpret_cast<const int4*>(slot);
         const double2* sc = reinterpret_cast<const double2*>(slot + (size_t)Lp * 4);
         fr->id = __ldg(ids + lane);
@@ -191,7 +191,7 @@ __device__ bool merge_node_seq(const MergeParams& P, const WarpTable<IdxT>& T, u
         add_entry(lane == 0 ? (int)(c & ~COL_SINK) : -1, (P.mode == MODE_GRANK) ? P.self_grank : 1.0);
         merged += (lane == 0);
       } else {
-        const unsigned char* slot = P.buf[read_slot[(c >> COL_COLOUR_SHIFT) & 1u]] + (size_t)(c & COL_POS_MASK) * slot_bytes(Lp);
+        const unsigned char* slot = P.buf[((c >> COL_COLOUR_SHIFT) & 1u) ? read_slot1 : read_slot0] + (size_t)(c & COL_POS_MASK) * slot_bytes(Lp);
         for (int g0 = 0; g0 < groups; g0 += 32) {
           BasketFrag fr;
           if (g0 == 0) fr = f0;
@@ -354,7 +354,7 @@ __device__ bool merge_node_seq(const MergeParams& P, const WarpTable<IdxT>& T, u
 // Persistent kernel: WARPS warps per CTA, each with a private CAP-slot table in shared memory
 // (CAP == 0: table in the global workspace `ws`, ws_cap slots per warp).
 template <int CAP, int WARPS, typename IdxT>
-__global__ void __launch_bounds__(WARPS * 32) merge_seq_kernel(MergeParams P, unsigned char* ws, unsigned int ws_cap,
+__global__ void __launch_bounds__(WARPS * 32, 1) merge_seq_kernel(MergeParams P, unsigned char* ws, unsigned int ws_cap,
                                                                int ws_identity) {
   extern __shared__ __align__(16) unsigned char smem[];
   RunState* st = P.st;
@@ -390,9 +390,7 @@ __global__ void __launch_bounds__(WARPS * 32) merge_seq_kernel(MergeParams P, un
   bool table_clean = false;  // cleared lazily: a warp that never gets work never touches its table
 
   const int write_slot = P.init_mode ? st->slot[P.colour] : (st->slot[P.colour] ^ 1);
-  int read_slot[2];
-  read_slot[0] = st->slot[0];
-  read_slot[1] = st->slot[1];
+  const int read_slot0 = st->slot[0], read_slot1 = st->slot[1];
 
   unsigned int total;
   if (P.queue_in_idx >= 0) total = st->qcount[P.queue_in_idx];
@@ -418,7 +416,7 @@ __global__ void __launch_bounds__(WARPS * 32) merge_seq_kernel(MergeParams P, un
       // class prediction: a node whose previous candidate count already exceeds this table goes straight on
       const bool skip = P.queue_out != nullptr && P.ncand[p] > P.limit;
       if (!skip)
-        ok = merge_node_seq<IdxT>(P, T, hist, s_count, p, write_slot, read_slot, s_merged, s_edges, s_cands, s_truncs,
+        ok = merge_node_seq<IdxT>(P, T, hist, s_count, p, write_slot, read_slot0, read_slot1, s_merged, s_edges, s_cands, s_truncs,
                                   s_ties, s_bytes, maxdiff);
       if (!ok) {
         if (lane == 0) {

@@ -7,7 +7,7 @@ scale=int(sys.argv[1]); hub=int(sys.argv[2]); iters=int(sys.argv[3]) if len(sys.
 g=G.rmat(scale); col=ppr.find_partitions_csr(g)
 s=ppr.Session(g,100,colour=col,hub_threshold=hub)
 lib=_lib.load()
-names=['fetch','setup','accum','redo','flush','select','write+norm','clear']
+names=['fetch','setup','accum/pass1','compact+tau(+redo)','pass2(+flush)','select','write+norm','clear']
 for rep in range(2):
     s.grank(50,100,iters,0.85,-1.0)
     st=s.stats(); l,ms=s.kernel_time(0)
