@@ -399,7 +399,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) merge_seq_kernel(MergeParams P,
   unsigned long long s_merged = 0, s_edges = 0, s_cands = 0, s_truncs = 0, s_ties = 0, s_bytes = 0, s_nodes = 0, s_requeue = 0;
   long long maxdiff = 0;
   // nodes are fetched in small batches: thousands of tiny nodes hammering one global counter would serialise there
-  const unsigned int batch = (P.queue_in_idx >= 0 || CAP == 0) ? 1u : 4u;
+  // (only when there are plenty of nodes per warp: with few nodes a batch would serialise them on a handful of warps)
+  const unsigned int batch = (P.queue_in_idx >= 0 || CAP == 0 || total < 16u * gridDim.x * WARPS) ? 1u : 4u;
   for (;;) {
     unsigned int idx0 = 0;
     if (lane == 0) idx0 = atomicAdd(&st->work[P.work_idx], batch);

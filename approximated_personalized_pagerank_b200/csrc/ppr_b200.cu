@@ -232,6 +232,12 @@ struct pprb200_session {
   std::vector<cudaEvent_t> ev_merge;  // pairs (begin,end) per iteration
   uint32_t merge_launches = 0;
   cudaEvent_t ev_walk[2] = {nullptr, nullptr};
+  // the three node classes of a colour (big, mid, exact-order cascade) are launched on three streams so that the tail of
+  // one persistent kernel overlaps the others; `cur` is the stream the launch helpers enqueue on
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaStream_t cur = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  bool overlap = true;
   unsigned long long* d_walk_ws = nullptr;  // fallback visit-count tables of the MC walk phase
   size_t walk_ws_bytes = 0;
   uint64_t launch_count = 0;  // kernels enqueued by the last run
@@ -302,6 +308,8 @@ static void session_free(pprb200_session* s) {
                    s->d_tbl_count, s->d_node_tbl, s->d_node_done};
   for (void* q : plain) dev_free(q);
   for (int i = 0; i < 2; i++) if (s->ev_walk[i]) cudaEventDestroy(s->ev_walk[i]);
+  for (int i = 0; i < 2; i++) { if (s->aux[i]) cudaStreamDestroy(s->aux[i]); if (s->ev_join[i]) cudaEventDestroy(s->ev_join[i]); }
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
   if (s->ev_begin) cudaEventDestroy(s->ev_begin);
   if (s->ev_end) cudaEventDestroy(s->ev_end);
   for (auto e : s->ev_merge) cudaEventDestroy(e);
@@ -548,6 +556,13 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   cudaEventCreate(&s->ev_end);
   cudaEventCreate(&s->ev_walk[0]);
   cudaEventCreate(&s->ev_walk[1]);
+  for (int i = 0; i < 2; i++) {
+    cudaStreamCreateWithFlags(&s->aux[i], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&s->ev_join[i], cudaEventDisableTiming);
+  }
+  cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
+  s->cur = s->stream;
+  if (const char* e = getenv("PPRB200_OVERLAP")) s->overlap = atoi(e) != 0;
   if (getenv("PPRB200_PROF")) {
     if ((rc = dev_alloc(&s->d_prof, (size_t)2 * s->sm_count * 8 * 8))) { session_free(s); return rc; }
     cudaMemsetAsync(s->d_prof, 0, (size_t)2 * s->sm_count * 8 * 8 * sizeof(unsigned long long), st);
@@ -578,7 +593,7 @@ static cudaError_t launch_stage(pprb200_session* s, const MergeParams& P, int gr
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  merge_seq_kernel<CAP, WARPS, IdxT><<<grid, WARPS * 32, smem, s->stream>>>(P, ws, ws_cap, ws_identity);
+  merge_seq_kernel<CAP, WARPS, IdxT><<<grid, WARPS * 32, smem, s->cur>>>(P, ws, ws_cap, ws_identity);
   s->launch_count++;
   return cudaGetLastError();
 }
@@ -635,10 +650,12 @@ static int enqueue_cascade(pprb200_session* s, MergeParams P, int range_begin, i
     int grid = std::max(1, gw / warps_g);
     const size_t need = (size_t)grid * warps_g * region;
     if (need > s->ws_bytes) {
+      g_alloc_stream = s->cur;  // stream-ordered with the launch below
       dev_free(s->d_ws);
       s->d_ws = nullptr;
       s->ws_bytes = 0;
       int rc = dev_alloc(&s->d_ws, need);
+      g_alloc_stream = s->stream;
       if (rc) return rc;
       s->ws_bytes = need;
     }
@@ -657,7 +674,7 @@ static cudaError_t launch_par(pprb200_session* s, const ParParams& P, int grid) 
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  merge_par_kernel<H, TCAP, CMAX, COLCAP, R, THREADS><<<grid, THREADS, smem, s->stream>>>(P);
+  merge_par_kernel<H, TCAP, CMAX, COLCAP, R, THREADS><<<grid, THREADS, smem, s->cur>>>(P);
   s->launch_count++;
   return cudaGetLastError();
 }
@@ -692,9 +709,32 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
     P.tbl_inuse = s->d_tbl_inuse + s->tbl_first[cls];
     P.tbl_count = s->d_tbl_count + s->tbl_first[cls];
     P.prof = s->d_prof ? s->d_prof + (size_t)cls * s->sm_count * 8 * 8 : nullptr;
+    s->cur = (s->overlap && cls == 0) ? s->aux[0] : s->stream;
     cudaError_t err = cls == 1 ? launch_par<8192, 2048, 3072, PAR_CHUNK_MAX, 8192, 512>(s, P, std::min(s->sm_count, e - b))
                                : launch_par<2048, 2048, 2048, PAR_MID_MAX, 0, 128>(s, P, std::min(s->sm_count * 3, e - b));
     if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_par launch failed: %s", cudaGetErrorString(err));
+  }
+  return PPRB200_OK;
+}
+
+// One colour's worth of merge work: big class on the session stream, mid class and the exact-order cascade on the two
+// auxiliary streams (fork / join through events), so that the three persistent kernels share the SMs as CTAs retire.
+static int enqueue_colour(pprb200_session* s, const MergeParams& Q, int c, int L) {
+  int rc;
+  if (s->overlap) {
+    cudaEventRecord(s->ev_fork, s->stream);
+    cudaStreamWaitEvent(s->aux[0], s->ev_fork, 0);
+    cudaStreamWaitEvent(s->aux[1], s->ev_fork, 0);
+  }
+  if ((rc = enqueue_par(s, Q, c, L))) return rc;
+  s->cur = s->overlap ? s->aux[1] : s->stream;
+  if (s->range_end[c] > s->range_begin[c] && (rc = enqueue_cascade(s, Q, s->range_begin[c], s->range_end[c], L))) return rc;
+  s->cur = s->stream;
+  if (s->overlap) {
+    for (int i = 0; i < 2; i++) {
+      cudaEventRecord(s->ev_join[i], s->aux[i]);
+      cudaStreamWaitEvent(s->stream, s->ev_join[i], 0);
+    }
   }
   return PPRB200_OK;
 }
@@ -782,8 +822,7 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
     for (int c = 0; c < 2; c++) {
       MergeParams Q = P;
       Q.init_mode = 1; Q.do_norm = 0; Q.colour = c;
-      if ((rc = enqueue_par(s, Q, c, (int)L))) return rc;
-      if (s->range_end[c] > s->range_begin[c] && (rc = enqueue_cascade(s, Q, s->range_begin[c], s->range_end[c], (int)L))) return rc;
+      if ((rc = enqueue_colour(s, Q, c, (int)L))) return rc;
       phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 1, 0, s->peers, c == 1);
       s->launch_count++;
     }
@@ -794,8 +833,7 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
     {
       MergeParams Q = P;
       Q.init_mode = 0; Q.do_norm = 1; Q.colour = c;
-      if ((rc = enqueue_par(s, Q, c, (int)L))) return rc;
-      if (s->range_end[c] > s->range_begin[c] && (rc = enqueue_cascade(s, Q, s->range_begin[c], s->range_end[c], (int)L))) return rc;
+      if ((rc = enqueue_colour(s, Q, c, (int)L))) return rc;
     }
     cudaEventRecord(s->ev_merge[2 * it + 1], st);
     iter_end_kernel<<<1, 1, 0, st>>>(s->d_state, c, tolerance, s->peers);
@@ -935,8 +973,7 @@ static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t 
       for (int c = 0; c < 2; c++) {
         MergeParams Q = P;
         Q.init_mode = 0; Q.do_norm = 0; Q.colour = c;
-        if ((rc = enqueue_par(s, Q, c, (int)L))) return rc;
-        if (s->range_end[c] > s->range_begin[c] && (rc = enqueue_cascade(s, Q, s->range_begin[c], s->range_end[c], (int)L))) return rc;
+        if ((rc = enqueue_colour(s, Q, c, (int)L))) return rc;
         // both colours read the same (old) buffer: counters are cleared between the two cascades, slots flip at the end
         phase_end_kernel<<<1, 1, 0, st>>>(s->d_state, 0, c == 1 ? 1 : 0, s->peers, c == 1);
         s->launch_count++;
