@@ -70,6 +70,16 @@ def make_graph(w):
     raise ValueError(w["gen"])
 
 
+def measured_traffic(workload, steps):
+    """DRAM bytes of the dominant kernels per step from the committed ncu capture of this command (profiles/traffic.json)"""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        t = json.loads(p.read_text()).get(workload)
+        return None if t is None else {"dram_bytes_per_step": t["dram_bytes_per_step"], "source": t["source"]}
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -401,7 +411,8 @@ def main():
     if w["kind"] == "mc":  # dominant kernel of the MC path by BASELINE's metric: the walk kernel (12 B per hop)
         rl_bytes, rl_ms, rl_kernel = walk_bytes, walk_ms, "mc_walk_kernel (12 B/hop + basket writes); combine rounds reported under roofline.combine"
     else:
-        rl_bytes, rl_ms, rl_kernel = abytes, merge_ms, "merge kernels (merge_par_kernel + merge_seq_kernel cascade), all launches of a step"
+        rl_bytes, rl_ms, rl_kernel = abytes, merge_ms, ("merge kernels (merge_par_kernel big/mid + merge_seq_kernel cascade, on three streams), "
+                                                        "all launches of a step; event-timed per iteration on the session stream")
     achieved = (rl_bytes / 1e9) / (rl_ms / 1e3) if rl_ms > 0 else None
     metric, unit = ("grank_node_iterations_per_s", "node-iterations/s") if w["kind"] == "grank" else ("mc_walk_steps_per_s", "walk-steps/s")
     line = {
@@ -414,7 +425,7 @@ def main():
                    "sharding": "single GPU" if world == 1 else f"sources sharded over {world} GPUs"},
         "wall_ms_per_step_incl_flush_and_stat_reads": wall_ms / steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                     "traffic": None, "peak_source": peak_src, "kernel": rl_kernel,
+                     "traffic": (measured_traffic(args.workload, steps) if world == 1 else None), "peak_source": peak_src, "kernel": rl_kernel,
                      "algorithmic_bytes_per_step": rl_bytes // steps, "kernel_ms_per_step": rl_ms / steps,
                      "share_of_step": rl_ms / dev_ms if dev_ms > 0 else None,
                      "combine": ({"achieved": (abytes / 1e9) / (merge_ms / 1e3) if merge_ms > 0 else None, "unit": "GB/s",

@@ -34,7 +34,7 @@ def main():
             sess.grank(K, L, it, 0.85, tol)
             got = sess.fetch()
             got.stats = sess.stats()
-            want = ob.oracle_grank(g, K, L, it, 0.85, tol, colour=colour, hub_threshold=hub if hub else 8)
+            want = ob.oracle_grank(g, K, L, it, 0.85, tol, colour=colour, hub_threshold=hub if hub else ppr.DEFAULT_HUB_THRESHOLD)
             assert_bit_identical(got, want, f"rank {rank}/{world} grank rmat{scale} hub {hub} K{K}")
             assert got.stats["iterations_run"] == want.stats["iterations_run"]
             t = torch.tensor([got.stats["merged_entries"], got.stats["nonsink_node_iterations"]], dtype=torch.int64, device="cuda")
@@ -45,7 +45,7 @@ def main():
             sess.mc(K, L, R, 0.85, rounds=rounds)
             got = sess.fetch()
             st = sess.stats()
-            want = ob.oracle_mc(g, K, L, R, 0.85, ppr.api.DEFAULT_MC_SEED, rounds, hub_threshold=hub if hub else 8)
+            want = ob.oracle_mc(g, K, L, R, 0.85, ppr.api.DEFAULT_MC_SEED, rounds, hub_threshold=hub if hub else ppr.DEFAULT_HUB_THRESHOLD)
             assert_bit_identical(got, want, f"rank {rank}/{world} mc rmat{scale} hub {hub} R{R}")
             t = torch.tensor([st["walk_steps"]], dtype=torch.int64, device="cuda")
             dist.all_reduce(t)

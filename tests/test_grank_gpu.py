@@ -72,7 +72,7 @@ def test_order_free_path_bit_identical_to_oracle(scale, hub, K, L, it, tol):
     g = G.rmat(scale)
     colour = ppr.find_partitions_csr(g)
     got = ppr.grank_csr(g, K, L, it, 0.85, tol, colour=colour, hub_threshold=hub)
-    want = ob.oracle_grank(g, K, L, it, 0.85, tol, colour=colour, hub_threshold=hub if hub else 8)
+    want = ob.oracle_grank(g, K, L, it, 0.85, tol, colour=colour, hub_threshold=hub if hub else ppr.DEFAULT_HUB_THRESHOLD)
     assert_bit_identical(got, want, f"rmat{scale} hub>{hub} K{K} L{L}")
     for k in HUB_STAT_KEYS:
         assert got.stats[k] == want.stats[k], (k, got.stats[k], want.stats[k])
