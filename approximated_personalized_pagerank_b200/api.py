@@ -22,7 +22,7 @@ from . import _lib
 from .graphs import CSRGraph, from_adjacency
 
 NEVER_HUB = 0xFFFFFFFF
-DEFAULT_HUB_THRESHOLD = 16  # PPRB200_DEFAULT_HUB_THRESHOLD (hub_threshold = 0 selects it)
+DEFAULT_HUB_THRESHOLD = 12  # PPRB200_DEFAULT_HUB_THRESHOLD (hub_threshold = 0 selects it)
 DEFAULT_MC_ROUNDS = 3
 DEFAULT_MC_SEED = 0x5EED5EED5EED5EED
 

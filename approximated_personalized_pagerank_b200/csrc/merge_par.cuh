@@ -57,37 +57,70 @@ struct ParShared {
   int out_pos;
   int ncand;
   unsigned int item;
-  unsigned long long red_a[16];
+  unsigned long long red_a[64];
   int sel_digit, sel_above, sel_cnt;
   unsigned int hist[256];
 };
 
+// CTA-wide reductions: warp shuffles, one shared-memory word per warp, then every warp folds the (<= 32) partial
+// results with shuffles again -- no serial loop over the warps. All threads must call; `scratch` holds >= 32 words.
 __device__ __forceinline__ unsigned long long block_reduce_min_ull(unsigned long long v, unsigned long long* scratch) {
   v = warp_min_ull(v);
+  const int nw = (int)(blockDim.x >> 5);
   if (lane_id() == 0) scratch[threadIdx.x >> 5] = v;
   __syncthreads();
-  unsigned long long r = scratch[0];
-  for (int i = 1; i < (int)(blockDim.x >> 5); i++) r = scratch[i] < r ? scratch[i] : r;
+  unsigned long long r = warp_min_ull(lane_id() < nw ? scratch[lane_id()] : ~0ull);
   __syncthreads();
   return r;
 }
 __device__ __forceinline__ unsigned long long block_reduce_max_ull(unsigned long long v, unsigned long long* scratch) {
   v = warp_max_ull(v);
+  const int nw = (int)(blockDim.x >> 5);
   if (lane_id() == 0) scratch[threadIdx.x >> 5] = v;
   __syncthreads();
-  unsigned long long r = scratch[0];
-  for (int i = 1; i < (int)(blockDim.x >> 5); i++) r = scratch[i] > r ? scratch[i] : r;
+  unsigned long long r = warp_max_ull(lane_id() < nw ? scratch[lane_id()] : 0ull);
   __syncthreads();
   return r;
 }
 __device__ __forceinline__ long long block_reduce_sum_ll(long long v, unsigned long long* scratch) {
   v = warp_sum_ll(v);
+  const int nw = (int)(blockDim.x >> 5);
   if (lane_id() == 0) scratch[threadIdx.x >> 5] = (unsigned long long)v;
   __syncthreads();
-  long long r = 0;
-  for (int i = 0; i < (int)(blockDim.x >> 5); i++) r += (long long)scratch[i];
+  long long r = warp_sum_ll(lane_id() < nw ? (long long)scratch[lane_id()] : 0ll);
   __syncthreads();
   return r;
+}
+// two reductions behind one pair of barriers: min of `a`, sum of `b`
+__device__ __forceinline__ void block_reduce_min_sum(unsigned long long& a, long long& b, unsigned long long* scratch) {
+  a = warp_min_ull(a);
+  b = warp_sum_ll(b);
+  const int nw = (int)(blockDim.x >> 5);
+  if (lane_id() == 0) { scratch[threadIdx.x >> 5] = a; scratch[32 + (threadIdx.x >> 5)] = (unsigned long long)b; }
+  __syncthreads();
+  a = warp_min_ull(lane_id() < nw ? scratch[lane_id()] : ~0ull);
+  b = warp_sum_ll(lane_id() < nw ? (long long)scratch[32 + lane_id()] : 0ll);
+  __syncthreads();
+}
+__device__ __forceinline__ void block_reduce_min_max(unsigned long long& a, unsigned long long& b, unsigned long long* scratch) {
+  a = warp_min_ull(a);
+  b = warp_max_ull(b);
+  const int nw = (int)(blockDim.x >> 5);
+  if (lane_id() == 0) { scratch[threadIdx.x >> 5] = a; scratch[32 + (threadIdx.x >> 5)] = b; }
+  __syncthreads();
+  a = warp_min_ull(lane_id() < nw ? scratch[lane_id()] : ~0ull);
+  b = warp_max_ull(lane_id() < nw ? scratch[32 + lane_id()] : 0ull);
+  __syncthreads();
+}
+__device__ __forceinline__ void block_reduce_sum2(long long& a, long long& b, unsigned long long* scratch) {
+  a = warp_sum_ll(a);
+  b = warp_sum_ll(b);
+  const int nw = (int)(blockDim.x >> 5);
+  if (lane_id() == 0) { scratch[threadIdx.x >> 5] = (unsigned long long)a; scratch[32 + (threadIdx.x >> 5)] = (unsigned long long)b; }
+  __syncthreads();
+  a = warp_sum_ll(lane_id() < nw ? (long long)scratch[lane_id()] : 0ll);
+  b = warp_sum_ll(lane_id() < nw ? (long long)scratch[32 + lane_id()] : 0ll);
+  __syncthreads();
 }
 
 // CTA-wide version of warp_radix_select (device_common.cuh); same contract (incl. the min/max probe from pass 3 on).
@@ -106,8 +139,7 @@ __device__ unsigned long long block_radix_select(int n, int k, KeyFn key, PredFn
     for (int u = 0; u < 4; u++)
       if (ok[u]) { lo = b[u] < lo ? b[u] : lo; hi = b[u] > hi ? b[u] : hi; cnt++; }
   }
-  lo = block_reduce_min_ull(lo, S->red_a);
-  hi = block_reduce_max_ull(hi, S->red_a);
+  block_reduce_min_max(lo, hi, S->red_a);
   *tie = false;
   *krem = 0;
   if (lo == hi) {
@@ -132,8 +164,7 @@ __device__ unsigned long long block_radix_select(int n, int k, KeyFn key, PredFn
         for (int u = 0; u < 4; u++)
           if (ok[u] && (b[u] & known) == prefix) { l2 = b[u] < l2 ? b[u] : l2; h2 = b[u] > h2 ? b[u] : h2; }
       }
-      l2 = block_reduce_min_ull(l2, S->red_a);
-      h2 = block_reduce_max_ull(h2, S->red_a);
+      block_reduce_min_max(l2, h2, S->red_a);
       if (l2 == h2) { *tie = true; *krem = k; if (ntied) *ntied = in_bucket; return l2; }
       const int t2 = 63 - __clzll((long long)(l2 ^ h2));
       known = ~((2ull << t2) - 1ull);
@@ -740,8 +771,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 3 : 1)) merge_par_k
       long long cntv = 0;
       for (int i = tid; i < Lp; i += THREADS)
         if (oid[i] >= 0) { const unsigned long long b = (unsigned long long)__double_as_longlong(osc[score_index(i, Lp)]); mn = b < mn ? b : mn; cntv++; }
-      mn = block_reduce_min_ull(mn, S->red_a);
-      cntv = block_reduce_sum_ll(cntv, S->red_a);
+      block_reduce_min_sum(mn, cntv, S->red_a);
       if (cntv >= L) theta0 = __longlong_as_double((long long)mn);
     }
     // compaction with the warm-start filter; returns the candidate count (S->ncand), positions start at S->ncand = 0
@@ -1013,8 +1043,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 3 : 1)) merge_par_k
             }
           }
         }
-        dsum = block_reduce_sum_ll(dsum, S->red_a);
-        old_cnt = (int)block_reduce_sum_ll(old_cnt, S->red_a);
+        long long oc = old_cnt;
+        block_reduce_sum2(dsum, oc, S->red_a);
+        old_cnt = (int)oc;
         if (tid == 0 && dsum > 0) atomicMax(&st->cur_max, dsum);
       }
       __syncthreads();

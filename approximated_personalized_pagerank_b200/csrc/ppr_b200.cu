@@ -316,9 +316,22 @@ static void session_free(pprb200_session* s) {
   delete s;
 }
 
-static int default_mid_deg() {
+// Largest out-degree of the mid class (128-thread CTAs, H = TCAP = 2048). The larger the label space, the larger the
+// share of tail labels per basket and the earlier the 2048-slot tail table fills up (measured on R-MAT 16..22,
+// profiles/r1/sweeps.txt): 64 up to 256 K nodes, 48 up to 2 M, 32 above.
+static int default_mid_deg(int32_t n) {
   if (const char* e = getenv("PPRB200_MID_DEG")) return std::min(PAR_MID_MAX, std::max(1, atoi(e)));
-  return 64;
+  return n <= (1 << 18) ? 64 : (n <= (1 << 21) ? 48 : 32);
+}
+
+// Successors per work item of the big class. A node above it is split into chunks that meet in a global table (single
+// pass, tail labels spill to L2) instead of taking the two-pass shared-memory scheme, which costs far more per entry
+// than it gains in balance: n/64 clamped to [2048, 32768] (measured: R-MAT-16 2048, -18 4096, -20 16384, -22 32768).
+static int default_chunk(int32_t n) {
+  if (const char* e = getenv("PPRB200_CHUNK")) return std::min(1 << 20, std::max(32, atoi(e)));
+  int c = 2048;
+  while (c < 32768 && (long long)c * 64 < (long long)n) c <<= 1;
+  return c;
 }
 
 // storage positions of the non-sink nodes: colour-major, then class (0 exact-order, 1 mid, 2 big), then out-degree
@@ -401,9 +414,8 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
 
   // storage order: colour-major; inside a colour the exact-order class first, then the order-free class
   // (mid, big); every class by out-degree descending (ties by dense id) -- big nodes first for load balance
-  s->chunk = n > 16 * 8192 ? 4096 : 1024;  // small graphs: finer items for load balance across the SMs
-  if (const char* e = getenv("PPRB200_CHUNK")) s->chunk = std::min(1 << 20, std::max(32, atoi(e)));
-  s->mid_deg = default_mid_deg();
+  s->chunk = default_chunk(n);
+  s->mid_deg = default_mid_deg(n);
   std::vector<int32_t> order;
   int cls_begin[2][3], cls_end[2][3];
   std::vector<int32_t> owner_of_pos;
@@ -1183,7 +1195,7 @@ int pprb200_shard_owner(const int64_t* row_ptr, const int32_t* col, int32_t n, c
   std::vector<int32_t> order;
   int cls_begin[2][3], cls_end[2][3];
   std::vector<int32_t> owner_of_pos;
-  storage_order(row_ptr, n, colour.data(), hub_threshold == 0 ? PPRB200_DEFAULT_HUB_THRESHOLD : hub_threshold, default_mid_deg(), order,
+  storage_order(row_ptr, n, colour.data(), hub_threshold == 0 ? PPRB200_DEFAULT_HUB_THRESHOLD : hub_threshold, default_mid_deg(n), order,
                 cls_begin, cls_end, world, &owner_of_pos);
   for (int32_t v = 0; v < n; v++) owner[v] = -1;
   for (size_t p = 0; p < order.size(); p++) owner[order[p]] = owner_of_pos[p];

@@ -42,7 +42,7 @@ extern "C" {
 #define PPRB200_ERR_STATE (-5)  /* session used in the wrong order */
 
 /* default out-degree above which a node is accumulated order-free in fixed point */
-#define PPRB200_DEFAULT_HUB_THRESHOLD 16u
+#define PPRB200_DEFAULT_HUB_THRESHOLD 12u
 #define PPRB200_DEFAULT_MC_ROUNDS 3u
 #define PPRB200_DEFAULT_MC_SEED 0x5eed5eed5eed5eedull
 
