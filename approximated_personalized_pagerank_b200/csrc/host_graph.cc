@@ -8,6 +8,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
+#include <condition_variable>
+#include <cstdlib>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -33,50 +37,239 @@ int validate_csr(const int64_t* row_ptr, const int32_t* col, int32_t n) {
   const int64_t e = row_ptr[n];
   if (e > 0 && !col) return fail(PPRB200_ERR_GRAPH, "col is NULL");
   if ((uint32_t)n > (1u << 30)) return fail(PPRB200_ERR_GRAPH, "n > 2^30 dense ids not supported");
-  for (int64_t i = 0; i < e; i++)
-    if (col[i] < 0 || col[i] >= n)
+  std::vector<int64_t> bad((size_t)host_threads(), -1);  // first offending edge of each range
+  host_parallel_for(e, 1 << 16, [&](int t, int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; i++)
+      if ((uint32_t)col[i] >= (uint32_t)n) { bad[(size_t)t] = i; break; }
+  });
+  for (const int64_t i : bad)
+    if (i >= 0)
       return fail(PPRB200_ERR_GRAPH, "successor %d at edge %lld is not a node of the graph (every sink must be a key, README.md:68-74)",
                   col[i], (long long)i);
   return PPRB200_OK;
 }
 
-// Reference semantics (pprInternal.h:29-99): predecessor lists are filled by scanning the map in
-// iteration order (= ascending dense id here) -> ascending source id with multiplicity; roots are taken in
-// iteration order and go to `first`; a popped node pushes its unvisited successors (vector order), then
-// its unvisited predecessors, all coloured opposite to itself. The queue is FIFO.
+// ---- worker pool ------------------------------------------------------------------------------------------------
+namespace {
+struct HostPool {
+  std::mutex m;
+  std::condition_variable cv_go, cv_done;
+  std::vector<std::thread> workers;
+  const std::function<void(int)>* fn = nullptr;
+  int parts = 0, next = 0, running = 0;
+  unsigned long long gen = 0;
+  std::mutex call;  // one parallel region at a time
+
+  explicit HostPool(int n) {
+    for (int i = 1; i < n; i++) {
+      workers.emplace_back([this]() {
+        unsigned long long seen = 0;
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+          cv_go.wait(lk, [&] { return gen != seen; });
+          seen = gen;
+          while (next < parts) {
+            const int part = next++;
+            running++;
+            lk.unlock();
+            (*fn)(part);
+            lk.lock();
+            running--;
+          }
+          if (running == 0) cv_done.notify_all();
+        }
+      });
+      workers.back().detach();
+    }
+  }
+  void run(int nparts, const std::function<void(int)>& f) {
+    std::lock_guard<std::mutex> serial(call);
+    std::unique_lock<std::mutex> lk(m);
+    fn = &f;
+    parts = nparts;
+    next = 0;
+    gen++;
+    cv_go.notify_all();
+    while (next < parts) {
+      const int part = next++;
+      running++;
+      lk.unlock();
+      f(part);
+      lk.lock();
+      running--;
+    }
+    cv_done.wait(lk, [&] { return running == 0 && next >= parts; });
+    parts = 0;
+    fn = nullptr;
+  }
+};
+
+int configured_threads() {
+  int t = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  if (const char* e = getenv("PPRB200_HOST_THREADS")) t = std::max(1, std::min(64, atoi(e)));
+  return t;
+}
+HostPool& pool() {
+  static HostPool* p = new HostPool(configured_threads());  // never destroyed: the workers are detached
+  return *p;
+}
+}  // namespace
+
+int host_threads() {
+  static const int t = configured_threads();
+  return t;
+}
+
+void host_parallel(int parts, const std::function<void(int)>& fn) {
+  if (parts <= 1 || host_threads() == 1) {
+    for (int i = 0; i < parts; i++) fn(i);
+    return;
+  }
+  pool().run(parts, fn);
+}
+
+void host_parallel_for(int64_t n, int64_t grain, const std::function<void(int, int64_t, int64_t)>& fn) {
+  if (n <= 0) return;
+  int parts = (int)std::min<int64_t>(host_threads(), (n + grain - 1) / grain);
+  if (parts <= 1) { fn(0, 0, n); return; }
+  host_parallel(parts, [&](int t) { fn(t, n * t / parts, n * (t + 1) / parts); });
+}
+
+void host_indegree(const int32_t* col, int64_t e, int32_t n, uint32_t* indeg) {
+  std::memset(indeg, 0, sizeof(uint32_t) * (size_t)n);
+  const int64_t grain = 1 << 16;
+  int parts = (int)std::min<int64_t>(host_threads(), (e + grain - 1) / grain);
+  // private histograms as long as they stay under 256 MB in total, else fewer threads
+  while (parts > 1 && (int64_t)parts * n * 4 > (256ll << 20)) parts--;
+  if (parts <= 1) {
+    for (int64_t i = 0; i < e; i++) indeg[(size_t)col[i]]++;
+    return;
+  }
+  std::vector<std::vector<uint32_t>> h((size_t)parts);
+  host_parallel(parts, [&](int t) {
+    h[(size_t)t].assign((size_t)n, 0u);
+    uint32_t* mine = h[(size_t)t].data();
+    for (int64_t i = e * t / parts, hi = e * (t + 1) / parts; i < hi; i++) mine[(size_t)col[i]]++;
+  });
+  host_parallel_for(n, 1 << 14, [&](int, int64_t lo, int64_t hi) {
+    for (int64_t v = lo; v < hi; v++) {
+      uint32_t sacc = 0;
+      for (int t = 0; t < parts; t++) sacc += h[(size_t)t][(size_t)v];
+      indeg[(size_t)v] = sacc;
+    }
+  });
+}
+
+// Reference semantics (pprInternal.h:29-99): roots are taken in map-iteration order (= ascending dense id here) and go
+// to `first`; a popped node colours its unvisited successors and predecessors opposite to itself; the queue is FIFO.
+// Hence colour(v) = parity of the undirected BFS distance from the root of v's component (the smallest dense id in
+// it), whatever the visiting order inside a level: the colouring below is level-synchronous, and the
+// levels of large components are expanded by all host threads. oracle/ppr_oracle.c keeps the literal FIFO version;
+// tests/test_host_logic.py compares the two.
 int find_partitions(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8_t* colour) {
   if (n == 0) return PPRB200_OK;
   const int64_t e = row_ptr[n];
+  const bool timing = getenv("PPRB200_HOST_TIMING") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
+  // predecessor lists (CSR transpose); node ranges balanced by edge count, private cursors per range
   std::vector<int64_t> prow((size_t)n + 1, 0);
-  std::vector<int32_t> pcol((size_t)e);
-  for (int64_t i = 0; i < e; i++) prow[(size_t)col[i] + 1]++;
-  for (int32_t v = 0; v < n; v++) prow[(size_t)v + 1] += prow[v];
+  std::vector<int32_t> pcol((size_t)std::max<int64_t>(e, 1));
   {
-    std::vector<int64_t> cursor(prow.begin(), prow.end() - 1);
-    for (int32_t u = 0; u < n; u++)
-      for (int64_t i = row_ptr[u]; i < row_ptr[u + 1]; i++) pcol[(size_t)cursor[col[i]]++] = u;
-  }
-  std::vector<uint8_t> seen((size_t)n, 0);
-  std::vector<int32_t> fifo((size_t)n);
-  for (int32_t root = 0; root < n; root++) {
-    if (seen[root]) continue;
-    size_t head = 0, tail = 0;
-    seen[root] = 1;
-    colour[root] = 0;
-    fifo[tail++] = root;
-    while (head < tail) {
-      const int32_t x = fifo[head++];
-      const uint8_t other = colour[x] ^ 1u;
-      for (int64_t i = row_ptr[x]; i < row_ptr[x + 1]; i++) {
-        const int32_t s = col[i];
-        if (!seen[s]) { seen[s] = 1; colour[s] = other; fifo[tail++] = s; }
-      }
-      for (int64_t i = prow[x]; i < prow[(size_t)x + 1]; i++) {
-        const int32_t p = pcol[(size_t)i];
-        if (!seen[p]) { seen[p] = 1; colour[p] = other; fifo[tail++] = p; }
-      }
+    int parts = (int)std::min<int64_t>(host_threads(), (e + (1 << 16) - 1) / (1 << 16));
+    while (parts > 1 && (int64_t)parts * n * 4 > (256ll << 20)) parts--;
+    if (parts <= 1) {
+      for (int64_t i = 0; i < e; i++) prow[(size_t)col[i] + 1]++;
+      for (int32_t v = 0; v < n; v++) prow[(size_t)v + 1] += prow[v];
+      std::vector<int64_t> cursor(prow.begin(), prow.end() - 1);
+      for (int32_t u = 0; u < n; u++)
+        for (int64_t i = row_ptr[u]; i < row_ptr[u + 1]; i++) pcol[(size_t)cursor[col[i]]++] = u;
+    } else {
+      std::vector<int32_t> cut((size_t)parts + 1, 0);  // node ranges with ~e/parts edges each
+      for (int t = 1; t < parts; t++)
+        cut[(size_t)t] = (int32_t)(std::lower_bound(row_ptr, row_ptr + n + 1, e * t / parts) - row_ptr);
+      cut[(size_t)parts] = n;
+      for (int t = 1; t <= parts; t++) cut[(size_t)t] = std::max(cut[(size_t)t], cut[(size_t)t - 1]);
+      std::vector<std::vector<uint32_t>> h((size_t)parts);
+      host_parallel(parts, [&](int t) {
+        h[(size_t)t].assign((size_t)n, 0u);
+        uint32_t* mine = h[(size_t)t].data();
+        for (int64_t i = row_ptr[cut[(size_t)t]], hi = row_ptr[cut[(size_t)t + 1]]; i < hi; i++) mine[(size_t)col[i]]++;
+      });
+      host_parallel_for(n, 1 << 14, [&](int, int64_t lo, int64_t hi) {
+        for (int64_t v = lo; v < hi; v++) {
+          uint32_t sacc = 0;
+          for (int t = 0; t < parts; t++) sacc += h[(size_t)t][(size_t)v];
+          prow[(size_t)v + 1] = sacc;
+        }
+      });
+      for (int32_t v = 0; v < n; v++) prow[(size_t)v + 1] += prow[v];
+      host_parallel_for(n, 1 << 14, [&](int, int64_t lo, int64_t hi) {  // counts -> first write offsets
+        for (int64_t v = lo; v < hi; v++) {
+          uint32_t run = 0;
+          for (int t = 0; t < parts; t++) { const uint32_t c = h[(size_t)t][(size_t)v]; h[(size_t)t][(size_t)v] = run; run += c; }
+        }
+      });
+      host_parallel(parts, [&](int t) {
+        uint32_t* mine = h[(size_t)t].data();
+        for (int32_t u = cut[(size_t)t]; u < cut[(size_t)t + 1]; u++)
+          for (int64_t i = row_ptr[u]; i < row_ptr[u + 1]; i++) {
+            const int32_t s = col[i];
+            pcol[(size_t)(prow[(size_t)s] + mine[(size_t)s]++)] = u;
+          }
+      });
     }
   }
+  const double t_transposed = now();
+  std::vector<uint8_t> seen((size_t)n, 0);
+  std::vector<int32_t> frontier, next;
+  const int T = host_threads();
+  std::vector<std::vector<int32_t>> local((size_t)T);
+  for (int32_t root = 0; root < n; root++) {
+    if (seen[(size_t)root]) continue;
+    seen[(size_t)root] = 1;
+    colour[root] = 0;
+    if (row_ptr[root + 1] == row_ptr[root] && prow[(size_t)root + 1] == prow[(size_t)root]) continue;  // isolated node
+    frontier.assign(1, root);
+    uint8_t other = 1;
+    while (!frontier.empty()) {
+      next.clear();
+      if (frontier.size() < 2048 || T == 1) {
+        for (const int32_t x : frontier) {
+          for (int64_t i = row_ptr[x]; i < row_ptr[x + 1]; i++) {
+            const int32_t s = col[i];
+            if (!seen[(size_t)s]) { seen[(size_t)s] = 1; colour[s] = other; next.push_back(s); }
+          }
+          for (int64_t i = prow[(size_t)x]; i < prow[(size_t)x + 1]; i++) {
+            const int32_t p = pcol[(size_t)i];
+            if (!seen[(size_t)p]) { seen[(size_t)p] = 1; colour[p] = other; next.push_back(p); }
+          }
+        }
+      } else {
+        const int64_t fs = (int64_t)frontier.size();
+        const int parts = (int)std::min<int64_t>(T, (fs + 511) / 512);
+        host_parallel(parts, [&](int t) {
+          std::vector<int32_t>& out = local[(size_t)t];
+          out.clear();
+          auto visit = [&](int32_t s) {
+            if (__atomic_load_n(&seen[(size_t)s], __ATOMIC_RELAXED)) return;
+            if (__atomic_exchange_n(&seen[(size_t)s], (uint8_t)1, __ATOMIC_RELAXED)) return;
+            colour[s] = other;
+            out.push_back(s);
+          };
+          for (int64_t k = fs * t / parts, hi = fs * (t + 1) / parts; k < hi; k++) {
+            const int32_t x = frontier[(size_t)k];
+            for (int64_t i = row_ptr[x]; i < row_ptr[x + 1]; i++) visit(col[i]);
+            for (int64_t i = prow[(size_t)x]; i < prow[(size_t)x + 1]; i++) visit(pcol[(size_t)i]);
+          }
+        });
+        for (int t = 0; t < parts; t++) next.insert(next.end(), local[(size_t)t].begin(), local[(size_t)t].end());
+      }
+      frontier.swap(next);
+      other ^= 1u;
+    }
+  }
+  if (timing) fprintf(stderr, "[pprb200] find_partitions: transpose %.2f ms, bfs %.2f ms (%d host threads)\n", t_transposed - t_begin, now() - t_transposed, host_threads());
   return PPRB200_OK;
 }
 

@@ -250,11 +250,16 @@ static int device_ok() {
     cudaGetLastError();
     return fail(PPRB200_ERR_CUDA, "no CUDA device available (libppr_b200 has no CPU fallback)");
   }
-  cudaDeviceProp pr;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (cudaGetDeviceProperties(&pr, dev) != cudaSuccess) return fail(PPRB200_ERR_CUDA, "cudaGetDeviceProperties failed");
-  if (pr.major != 10) return fail(PPRB200_ERR_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only", pr.name, pr.major, pr.minor);
+  static int checked_dev = -1;  // cudaGetDeviceProperties costs a millisecond or two: ask once per device
+  if (dev == checked_dev) return PPRB200_OK;
+  int major = 0, minor = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess)
+    return fail(PPRB200_ERR_CUDA, "cudaDeviceGetAttribute failed");
+  if (major != 10) return fail(PPRB200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, major, minor);
+  checked_dev = dev;
   return PPRB200_OK;
 }
 
@@ -341,23 +346,31 @@ static int default_chunk(int32_t n) {
 static void storage_order(const int64_t* row_ptr, int32_t n, const uint8_t* colour, uint32_t hub_threshold, int mid_deg,
                           std::vector<int32_t>& order, int cls_begin[2][3], int cls_end[2][3], int world = 1,
                           std::vector<int32_t>* owner_of_pos = nullptr) {
-  order.clear();
-  order.reserve((size_t)n);
+  // one counting sort on the key (colour, class, out-degree descending); nodes are scattered in ascending id order, so
+  // ties keep it
+  int64_t max_d = 0;
+  for (int32_t v = 0; v < n; v++) max_d = std::max<int64_t>(max_d, row_ptr[v + 1] - row_ptr[v]);
+  const size_t per_group = (size_t)max_d + 1;
+  std::vector<int32_t> start(6 * per_group + 1, 0);
+  auto key_of = [&](int32_t v, int64_t d) -> size_t {
+    const int cls = (uint64_t)d <= (uint64_t)hub_threshold ? 0 : (d <= mid_deg ? 1 : 2);
+    return ((size_t)colour[v] * 3 + (size_t)cls) * per_group + (size_t)(max_d - d);
+  };
+  for (int32_t v = 0; v < n; v++) {
+    const int64_t d = row_ptr[v + 1] - row_ptr[v];
+    if (d > 0) start[key_of(v, d) + 1]++;
+  }
+  for (size_t i = 0; i < 6 * per_group; i++) start[i + 1] += start[i];
   for (int c = 0; c < 2; c++)
     for (int cls = 0; cls < 3; cls++) {
-      const size_t b = order.size();
-      cls_begin[c][cls] = (int)b;
-      for (int32_t v = 0; v < n; v++) {
-        const int64_t d = row_ptr[v + 1] - row_ptr[v];
-        if (colour[v] != c || d == 0) continue;
-        const int k = (uint64_t)d <= (uint64_t)hub_threshold ? 0 : (d <= mid_deg ? 1 : 2);
-        if (k == cls) order.push_back(v);
-      }
-      std::stable_sort(order.begin() + (long)b, order.end(), [&](int32_t x, int32_t y) {
-        return (row_ptr[x + 1] - row_ptr[x]) > (row_ptr[y + 1] - row_ptr[y]);
-      });
-      cls_end[c][cls] = (int)order.size();
+      cls_begin[c][cls] = start[((size_t)c * 3 + (size_t)cls) * per_group];
+      cls_end[c][cls] = start[((size_t)c * 3 + (size_t)cls + 1) * per_group];
     }
+  order.assign((size_t)start[6 * per_group], 0);
+  for (int32_t v = 0; v < n; v++) {
+    const int64_t d = row_ptr[v + 1] - row_ptr[v];
+    if (d > 0) order[(size_t)start[key_of(v, d)]++] = v;
+  }
   if (owner_of_pos) {
     owner_of_pos->assign(order.size(), 0);
     if (world > 1)
@@ -412,6 +425,7 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
     s->colour_count[colour[v]]++;
   }
 
+  const double t_col = now_ms();
   // storage order: colour-major; inside a colour the exact-order class first, then the order-free class
   // (mid, big); every class by out-degree descending (ties by dense id) -- big nodes first for load balance
   s->chunk = default_chunk(n);
@@ -432,15 +446,24 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
       s->range_end[c] = (int)seq_list.size();
     }
   }
-  // rank labels: in-degree descending, ties by dense id (the keys stored in the baskets)
+  const double t_ord = now_ms();
+  // rank labels: in-degree descending, ties by dense id (the keys stored in the baskets) -- a counting sort
   std::vector<int32_t> dense_of((size_t)n), rank_of((size_t)n);
   {
-    std::vector<int64_t> indeg((size_t)n, 0);
-    for (int64_t i = 0; i < row_ptr[n]; i++) indeg[(size_t)col[i]]++;
-    std::iota(dense_of.begin(), dense_of.end(), 0);
-    std::stable_sort(dense_of.begin(), dense_of.end(), [&](int32_t x, int32_t y) { return indeg[x] > indeg[y]; });
-    for (int32_t r = 0; r < n; r++) rank_of[(size_t)dense_of[r]] = r;
+    std::vector<uint32_t> indeg((size_t)n);
+    host_indegree(col, row_ptr[n], n, indeg.data());
+    uint32_t max_in = 0;
+    for (int32_t v = 0; v < n; v++) max_in = std::max(max_in, indeg[(size_t)v]);
+    std::vector<int32_t> start((size_t)max_in + 2, 0);
+    for (int32_t v = 0; v < n; v++) start[(size_t)(max_in - indeg[(size_t)v]) + 1]++;
+    for (size_t i = 0; i <= (size_t)max_in; i++) start[i + 1] += start[i];
+    for (int32_t v = 0; v < n; v++) {
+      const int32_t r = start[(size_t)(max_in - indeg[(size_t)v])]++;
+      dense_of[(size_t)r] = v;
+      rank_of[(size_t)v] = r;
+    }
   }
+  const double t_rank = now_ms();
   const int32_t M = (int32_t)order.size();
   s->M = M;
   std::vector<int32_t> pos_of((size_t)n, -1);
@@ -475,17 +498,31 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   for (int c = 0; c < 2; c++)
     for (int p = cls_begin[c][0]; p < cls_end[c][0]; p++)
       s->max_deg_seq = std::max<int32_t>(s->max_deg_seq, (int32_t)std::min<long long>(row_off[(size_t)p + 1] - row_off[p], INT32_MAX));
+  const double t_items = now_ms();
+  // column words: one lookup table (word of every node), then a parallel gather over edge-balanced position ranges
   std::vector<uint32_t> enc((size_t)std::max<int64_t>(E, 1));
-  for (int32_t p = 0; p < M; p++) {
-    const int32_t v = order[p];
-    long long o = row_off[p];
-    for (int64_t i = row_ptr[v]; i < row_ptr[v + 1]; i++) {
-      const int32_t su = col[i];
-      enc[(size_t)o++] = pos_of[su] < 0 ? (COL_SINK | (uint32_t)rank_of[su])
-                                         : ((uint32_t)pos_of[su] | ((uint32_t)colour[su] << COL_COLOUR_SHIFT));
-    }
+  {
+    std::vector<uint32_t> word_of((size_t)n);
+    host_parallel_for(n, 1 << 15, [&](int, int64_t lo, int64_t hi) {
+      for (int64_t v = lo; v < hi; v++)
+        word_of[(size_t)v] = pos_of[(size_t)v] < 0 ? (COL_SINK | (uint32_t)rank_of[(size_t)v])
+                                                    : ((uint32_t)pos_of[(size_t)v] | ((uint32_t)colour[(size_t)v] << COL_COLOUR_SHIFT));
+    });
+    const int parts = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), E / (1 << 15)));
+    host_parallel(parts, [&](int t) {
+      const int32_t p_lo = (int32_t)(std::lower_bound(row_off.begin(), row_off.end(), (long long)(E * t / parts)) - row_off.begin());
+      const int32_t p_hi = t + 1 == parts ? M : (int32_t)(std::lower_bound(row_off.begin(), row_off.end(), (long long)(E * (t + 1) / parts)) - row_off.begin());
+      for (int32_t p = p_lo; p < p_hi; p++) {
+        const int32_t v = order[(size_t)p];
+        long long o = row_off[(size_t)p];
+        for (int64_t i = row_ptr[v]; i < row_ptr[v + 1]; i++) enc[(size_t)o++] = word_of[(size_t)col[i]];
+      }
+    });
   }
   s->prep_ms = now_ms() - t0;
+  if (getenv("PPRB200_HOST_TIMING"))
+    fprintf(stderr, "[pprb200] host prep %.2f ms: colour %.2f, storage order %.2f, rank labels %.2f, offsets+items %.2f, encode %.2f (%d threads)\n",
+            s->prep_ms, t_col - t0, t_ord - t_col, t_rank - t_ord, t_items - t_rank, now_ms() - t_items, host_threads());
 
   const double t1 = now_ms();
   const int Lp = roundup4((int)max_L);
@@ -580,6 +617,7 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
     cudaMemsetAsync(s->d_prof, 0, (size_t)2 * s->sm_count * 8 * 8 * sizeof(unsigned long long), st);
   }
   s->h2d_ms = now_ms() - t1;
+  if (getenv("PPRB200_HOST_TIMING")) fprintf(stderr, "[pprb200] device setup + H2D %.2f ms\n", s->h2d_ms);
   *out = s;
   return PPRB200_OK;
 }
@@ -1221,11 +1259,14 @@ int pprb200_grank(const int64_t* row_ptr, const int32_t* col, int32_t n, const u
     std::lock_guard<std::mutex> lk(g_api_mutex);
     rc = session_create_impl(row_ptr, col, n, colour, L, hub_threshold, 0, 1, nullptr, &s);
     if (rc) return rc;
+    const double t_created = now_ms();
     rc = session_grank_impl(s, K, L, iterations, damping, tolerance);
     double t_d2h = 0;
+    const double t_enq = now_ms();
+    double t_run = t_enq;
     if (!rc) {
       cudaStreamSynchronize(s->stream);
-      const double t1 = now_ms();
+      const double t1 = t_run = now_ms();
       rc = session_fetch_impl(s, out_ids, out_scores, out_cnt);
       t_d2h = now_ms() - t1;
     }
@@ -1233,7 +1274,11 @@ int pprb200_grank(const int64_t* row_ptr, const int32_t* col, int32_t n, const u
       rc = session_stats_impl(s, stats);
       stats->d2h_ms = t_d2h;
     }
+    const double t_f0 = now_ms();
     session_free(s);
+    if (getenv("PPRB200_HOST_TIMING"))
+      fprintf(stderr, "[pprb200] grank call: create %.2f ms, enqueue %.2f, wait %.2f, fetch %.2f, stats %.2f, free %.2f\n", t_created - t0,
+              t_enq - t_created, t_run - t_enq, t_d2h, t_f0 - t_run - t_d2h, now_ms() - t_f0);
   }
   if (!rc && stats) stats->total_ms = now_ms() - t0;
   return rc;

@@ -3,6 +3,7 @@
 #define PPRB200_INTERNAL_H
 
 #include <cstdint>
+#include <functional>
 
 #include "../../include/pprb200.h"
 
@@ -13,6 +14,17 @@ int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
 
 int validate_csr(const int64_t* row_ptr, const int32_t* col, int32_t n);
 int find_partitions(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8_t* colour);
+
+// ---- host-side parallelism (the front half of a call: colouring, storage order, CSR encode) ----
+// Worker threads are created once per process and reused (PPRB200_HOST_THREADS, default min(hardware threads, 16)).
+// host_parallel(parts, fn) runs fn(part) for part = 0..parts-1 on the pool (the caller takes part in the work) and
+// returns when all are done; parts <= host_threads(). Calls are serialised.
+int host_threads();
+void host_parallel(int parts, const std::function<void(int)>& fn);
+// splits [0, n) into `parts` ranges and runs fn(part, lo, hi); runs inline when n is small or parts == 1
+void host_parallel_for(int64_t n, int64_t grain, const std::function<void(int, int64_t, int64_t)>& fn);
+// in-degree of every node (multiplicity counted), parallel
+void host_indegree(const int32_t* col, int64_t e, int32_t n, uint32_t* indeg);
 
 }  // namespace pprb200
 
