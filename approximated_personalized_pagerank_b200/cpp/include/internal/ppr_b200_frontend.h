@@ -18,6 +18,7 @@
 #ifndef PPR_B200_FRONTEND_H
 #define PPR_B200_FRONTEND_H
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <iostream>
@@ -52,8 +53,24 @@ struct DenseGraph {
   std::vector<int32_t> col;
 };
 
+inline size_t hostThreads() {
+  const unsigned hc = std::thread::hardware_concurrency();
+  return hc ? hc : 1;
+}
+
+// runs fn(begin, end) over [0, n) on up to `threads` std::threads (inline when the range is small)
+template <typename Fn>
+inline void parallelRanges(size_t n, size_t threads, size_t grain, Fn fn) {
+  const size_t parts = std::min(threads ? threads : 1, (n + grain - 1) / (grain ? grain : 1));
+  if (parts <= 1) { fn((size_t)0, n); return; }
+  std::vector<std::thread> pool;
+  for (size_t t = 1; t < parts; t++) pool.emplace_back(fn, n * t / parts, n * (t + 1) / parts);
+  fn((size_t)0, n / parts);
+  for (auto& th : pool) th.join();
+}
+
 template <typename Key>
-DenseGraph<Key> relabel(const std::unordered_map<Key, std::vector<Key>>& graph) {
+DenseGraph<Key> relabel(const std::unordered_map<Key, std::vector<Key>>& graph, size_t threads = hostThreads()) {
   DenseGraph<Key> g;
   const size_t n = graph.size();
   if (n > (size_t)1 << 30) die("graphs with more than 2^30 nodes are not supported");
@@ -61,22 +78,29 @@ DenseGraph<Key> relabel(const std::unordered_map<Key, std::vector<Key>>& graph) 
   g.rowPtr.reserve(n + 1);
   std::unordered_map<Key, int32_t> idOf;
   idOf.reserve(n);
-  size_t edges = 0;
+  std::vector<const std::vector<Key>*> succOf;
+  succOf.reserve(n);
+  g.rowPtr.push_back(0);
   for (const auto& kv : graph) {  // map iteration order defines the dense ids
     idOf.emplace(kv.first, (int32_t)g.keyOf.size());
     g.keyOf.push_back(&kv.first);
-    edges += kv.second.size();
+    succOf.push_back(&kv.second);
+    g.rowPtr.push_back(g.rowPtr.back() + (int64_t)kv.second.size());
   }
-  g.col.reserve(edges);
-  g.rowPtr.push_back(0);
-  for (const auto& kv : graph) {
-    for (const Key& s : kv.second) {
-      const auto it = idOf.find(s);
-      if (it == idOf.end()) die("successor is not a key of the graph: nodes without edges must be mapped to an empty vector");
-      g.col.push_back(it->second);
+  g.col.resize((size_t)g.rowPtr.back());
+  // the successor lookups (one hash find per edge) only read idOf: node ranges in parallel
+  std::vector<char> missing(1, 0);
+  parallelRanges(n, threads, 4096, [&](size_t begin, size_t end) {
+    for (size_t v = begin; v < end; v++) {
+      int64_t o = g.rowPtr[v];
+      for (const Key& s : *succOf[v]) {
+        const auto it = idOf.find(s);
+        if (it == idOf.end()) { missing[0] = 1; return; }
+        g.col[(size_t)o++] = it->second;
+      }
     }
-    g.rowPtr.push_back((int64_t)g.col.size());
-  }
+  });
+  if (missing[0]) die("successor is not a key of the graph: nodes without edges must be mapped to an empty vector");
   return g;
 }
 
@@ -111,9 +135,68 @@ std::unordered_map<Key, std::unordered_map<Key, double>> materialise(const Dense
   return out;
 }
 
-inline size_t hostThreads() {
-  const unsigned hc = std::thread::hardware_concurrency();
-  return hc ? hc : 1;
+// ---- flat result view ---------------------------------------------------------------------------
+// At a million nodes and more, building n * K hash-map entries on the host costs more than the kernels. FlatBaskets
+// is the same result without the maps: node v (dense id = position in the caller's map iteration order) has
+// cnt[v] <= K entries ids[v*K + i] / scores[v*K + i], sorted by (score descending, dense id ascending); key(v) maps a
+// dense id back to the caller's key. toMaps() gives the reference's return type.
+template <typename Key>
+struct FlatBaskets {
+  size_t K = 0;
+  std::vector<const Key*> keyOf;  // pointers into the caller's graph: valid while the graph is
+  std::vector<int32_t> ids;
+  std::vector<double> scores;
+  std::vector<uint32_t> cnt;
+  size_t size() const { return keyOf.size(); }
+  const Key& key(size_t denseId) const { return *keyOf[denseId]; }
+  std::unordered_map<Key, std::unordered_map<Key, double>> toMaps(size_t threads = hostThreads()) const {
+    DenseGraph<Key> g;
+    g.keyOf = keyOf;
+    return materialise(g, K, ids, scores, cnt, threads);
+  }
+};
+
+template <typename Key>
+FlatBaskets<Key> grankFlat(const std::unordered_map<Key, std::vector<Key>>& graph, size_t K, size_t L, size_t iterations,
+                           double damping, double tolerance) {
+  checkParameters(K, L, iterations, damping);
+  FlatBaskets<Key> out;
+  out.K = K;
+  if (graph.empty()) return out;
+  if (K > 0xffffffffu || L > 0xffffffffu || iterations > 0xffffffffu) die("K, L and iterations must fit 32 bits");
+  DenseGraph<Key> g = relabel(graph);
+  const size_t n = g.keyOf.size();
+  out.ids.resize(n * K);
+  out.scores.resize(n * K);
+  out.cnt.resize(n);
+  const int rc = pprb200_grank(g.rowPtr.data(), g.col.data(), (int32_t)n, NULL, (uint32_t)K, (uint32_t)L, (uint32_t)iterations,
+                               damping, tolerance, 0, out.ids.data(), out.scores.data(), out.cnt.data(), NULL);
+  if (rc != PPRB200_OK) die(pprb200_last_error());
+  out.keyOf.swap(g.keyOf);
+  return out;
+}
+
+template <typename Key>
+FlatBaskets<Key> mccompletepathv2Flat(const std::unordered_map<Key, std::vector<Key>>& graph, size_t K, size_t L,
+                                      size_t iterations, double damping) {
+  checkParameters(K, L, iterations, damping);
+  FlatBaskets<Key> out;
+  out.K = K;
+  if (graph.empty()) return out;
+  if (K > 0xffffffffu || L > 0xffffffffu || iterations > 0xffffffffu) die("K, L and iterations must fit 32 bits");
+  DenseGraph<Key> g = relabel(graph);
+  const size_t n = g.keyOf.size();
+  out.ids.resize(n * K);
+  out.scores.resize(n * K);
+  out.cnt.resize(n);
+  uint64_t seed = PPRB200_DEFAULT_MC_SEED;
+  if (const char* e = std::getenv("PPRB200_MC_SEED")) seed = std::strtoull(e, NULL, 0);
+  const int rc = pprb200_mccompletepathv2(g.rowPtr.data(), g.col.data(), (int32_t)n, (uint32_t)K, (uint32_t)L, (uint32_t)iterations,
+                                          damping, seed, PPRB200_DEFAULT_MC_ROUNDS, 0, out.ids.data(), out.scores.data(),
+                                          out.cnt.data(), NULL);
+  if (rc != PPRB200_OK) die(pprb200_last_error());
+  out.keyOf.swap(g.keyOf);
+  return out;
 }
 
 template <typename Key>

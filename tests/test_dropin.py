@@ -95,3 +95,10 @@ def test_mc_structural_cases_hold_for_both_builds():
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
     if REF.exists():
         assert run(REF, "mc_structural").returncode == 0
+
+
+@pytest.mark.gpu
+def test_flat_result_view_holds_what_the_maps_hold():
+    """SURVEY.md 8-f1: ppr::b200::grankFlat / mccompletepathv2Flat (no n*K hash inserts) == the reference-typed maps."""
+    r = run(ROOT / "tests" / "cpp" / "flat_check_b200")
+    assert r.returncode == 0 and "flat_check OK" in r.stdout, r.stdout + r.stderr
