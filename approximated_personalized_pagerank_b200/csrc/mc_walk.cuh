@@ -68,31 +68,38 @@ __device__ __forceinline__ uint32_t hash_word(uint32_t w) {
   return x ^ (x >> 15);
 }
 
+constexpr int WALK_CH = 1024;  // bins of the visit-count histogram that finds the top-L cut in one pass
+
 struct WalkShared {
   ParShared P;               // scratch of block_radix_select
   unsigned int next_walk;
   unsigned int ndistinct;
   int overflow;
   unsigned int item;
+  int cut_count, cut_above, cut_ties;
+  unsigned int chist[WALK_CH];
 };
 
 template <bool GLOBAL, int THREADS>
-__global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
+__global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : 3)) mc_walk_kernel(WalkParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   RunState* st = P.st;
   WalkShared* S = reinterpret_cast<WalkShared*>(smem);
-  // fallback tables are large (sized for the worst case) and sparsely used: their occupied slots are tracked in a list so
-  // that clearing and selecting cost O(distinct visited), not O(capacity)
+  // The occupied slots of the table are tracked in a first-touch list, so that selecting, writing and clearing cost
+  // O(distinct visited nodes), not O(capacity). Shared-memory tables: 16-bit list behind the table; fallback tables
+  // (global workspace, sized for the worst case): 32-bit list behind the table. The capacity need not be a power of two.
   unsigned char* gbase = GLOBAL ? reinterpret_cast<unsigned char*>(P.ws) + (size_t)blockIdx.x * P.tcap * (sizeof(WalkSlot) + sizeof(unsigned int)) : nullptr;
   WalkSlot* tbl = GLOBAL ? reinterpret_cast<WalkSlot*>(gbase)
                          : reinterpret_cast<WalkSlot*>(smem + ((sizeof(WalkShared) + 15) & ~(size_t)15));
   unsigned int* glist = GLOBAL ? reinterpret_cast<unsigned int*>(gbase + (size_t)P.tcap * sizeof(WalkSlot)) : nullptr;
-  if (GLOBAL) {
-    for (unsigned int i = threadIdx.x; i < P.tcap; i += THREADS) { tbl[i].key = WALK_EMPTY; tbl[i].count = 0u; }
-    __syncthreads();
-  }
+  unsigned short* slist = GLOBAL ? nullptr : reinterpret_cast<unsigned short*>(reinterpret_cast<unsigned char*>(tbl) + (size_t)P.tcap * sizeof(WalkSlot));
+  auto list_set = [&](unsigned int i, unsigned int h) { if (GLOBAL) glist[i] = h; else slist[i] = (unsigned short)h; };
+  auto list_get = [&](unsigned int i) -> unsigned int { return GLOBAL ? glist[i] : (unsigned int)slist[i]; };
+  for (unsigned int i = threadIdx.x; i < P.tcap; i += THREADS) { tbl[i].key = WALK_EMPTY; tbl[i].count = 0u; }
+  __syncthreads();
   const int tid = threadIdx.x;
-  const unsigned int mask = P.tcap - 1u;
+  const unsigned int cap = P.tcap;
+  auto slot0 = [&](uint32_t word) -> unsigned int { return __umulhi(hash_word(word), cap); };
   const int Lp = P.Lp, L = P.L;
   const double inv_r_den = (double)P.R;
 
@@ -116,15 +123,12 @@ __global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
     const uint32_t src_dense = (uint32_t)P.g.dense_of[self_label];
     const uint32_t self_word = (uint32_t)p | ((uint32_t)P.colour[src_dense] << COL_COLOUR_SHIFT);
 
-    if (!GLOBAL)
-      for (unsigned int i = tid; i < P.tcap; i += THREADS) { tbl[i].key = WALK_EMPTY; tbl[i].count = 0u; }
-    if (tid == 0) { S->next_walk = 0u; S->ndistinct = 1u; S->overflow = 0; }
-    __syncthreads();
-    if (tid == 0) {  // res[src] = R (mccompletepathv2.h:124)
-      const unsigned int h = hash_word(self_word) & mask;
+    if (tid == 0) {  // res[src] = R (mccompletepathv2.h:124); the table is empty here
+      S->next_walk = 0u; S->ndistinct = 1u; S->overflow = 0;
+      const unsigned int h = slot0(self_word);
       tbl[h].key = self_word;
       tbl[h].count = P.R;
-      if (GLOBAL) glist[0] = h;
+      list_set(0u, h);
     }
     __syncthreads();
 
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
         const unsigned long long deg = (unsigned long long)(re - rb);
         const uint32_t word = P.g.col[rb + (long long)(((unsigned long long)a * deg) >> 32)];  // :149, random successor
         // count the visit (:152-153 without the cap)
-        unsigned int h = hash_word(word) & mask;
+        unsigned int h = slot0(word);
         for (;;) {
           const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&tbl[h].key);
           if (cur == word) break;
@@ -152,13 +156,13 @@ __global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
             const uint32_t old = atomicCAS(&tbl[h].key, WALK_EMPTY, word);
             if (old == WALK_EMPTY) {
               const unsigned int pos = atomicAdd(&S->ndistinct, 1u);
-              if (GLOBAL) glist[pos] = h;
+              list_set(pos, h);
               if (pos + 1u > P.limit) S->overflow = 1;
               break;
             }
             if (old == word) break;
           }
-          h = (h + 1u) & mask;
+          h = h + 1u == cap ? 0u : h + 1u;
         }
         atomicAdd(&tbl[h].count, 1u);
         steps++;
@@ -170,6 +174,8 @@ __global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
     }
     __syncthreads();
     if (S->overflow) {
+      const unsigned int nd = S->ndistinct;
+      for (unsigned int i = tid; i < nd; i += THREADS) { const unsigned int h = list_get(i); tbl[h].key = WALK_EMPTY; tbl[h].count = 0u; }
       if (tid == 0) {
         const unsigned int q = atomicAdd(&st->qcount[P.queue_out_idx], 1u);
         P.queue_out[q] = (unsigned int)p;
@@ -180,9 +186,12 @@ __global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
     }
 
     // ---- top-L on (count desc, dense id asc), scores = count / R (:159-160) ----
+    // Visit counts are small integers: one pass over the first-touch list fills a histogram of min(count, WALK_CH - 1),
+    // a warp finds the cut. (A cut inside the last bin -- at least L nodes visited >= WALK_CH - 1 times -- takes the radix
+    // select.) Ties on the cut count are broken by dense id with a radix select over the tied entries only.
     const int n = (int)S->ndistinct;
-    const int nscan = GLOBAL ? n : (int)P.tcap;                                 // candidates are scanned through the list / the table
-    auto slot_at = [&](int i) -> unsigned int { return GLOBAL ? glist[i] : (unsigned int)i; };
+    const int nscan = n;
+    auto slot_at = [&](int i) -> unsigned int { return list_get((unsigned int)i); };
     auto word_label = [&](uint32_t wd) -> int { return (wd & COL_SINK) ? (int)(wd & ~COL_SINK) : P.g.label[wd & COL_POS_MASK]; };
     Threshold th;
     th.bits = 0ull;
@@ -190,15 +199,66 @@ __global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
     int kept = n;
     if (n > L) {
       kept = L;
-      bool tie;
-      int krem;
-      auto occupied = [&](int i) { return tbl[slot_at(i)].key != WALK_EMPTY; };
-      auto keyfn = [&](int i) { return (unsigned long long)tbl[slot_at(i)].count; };
-      th.bits = block_radix_select(nscan, L, keyfn, occupied, &S->P, &tie, &krem);
+      bool tie = false;
+      int krem = 0, ntied = 0;
+      for (int i = tid; i < WALK_CH; i += THREADS) S->chist[i] = 0u;
+      __syncthreads();
+      {
+        // most nodes are visited once or a few times: those bins are counted in registers (thousands of shared-memory
+        // atomics on one address would serialise), the rest with atomics
+        int small[4] = {0, 0, 0, 0};
+        for (int i = tid; i < n; i += THREADS) {
+          const unsigned int c = tbl[slot_at(i)].count;
+          if (c >= 1u && c <= 4u) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) small[j] += (c == (unsigned)(j + 1));
+          } else {
+            atomicAdd(&S->chist[c < (unsigned)(WALK_CH - 1) ? c : (unsigned)(WALK_CH - 1)], 1u);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int t = warp_sum_int(small[j]);
+          if ((tid & 31) == 0 && t) atomicAdd(&S->chist[j + 1], (unsigned int)t);
+        }
+      }
+      __syncthreads();
+      if (tid < 32) {
+        constexpr int PER = WALK_CH / 32;
+        unsigned int local = 0;
+        for (int j = 0; j < PER; j++) local += S->chist[tid * PER + j];
+        unsigned int incl = local;  // entries in the bins of this lane and of all higher lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int t = __shfl_down_sync(FULL, incl, o);
+          if (tid + o < 32) incl += t;
+        }
+        const unsigned int above = incl - local;
+        if (above < (unsigned)L && incl >= (unsigned)L) {
+          unsigned int run = above;
+          for (int j = PER - 1; j >= 0; j--) {
+            const unsigned int c = S->chist[tid * PER + j];
+            if (run < (unsigned)L && run + c >= (unsigned)L) { S->cut_count = tid * PER + j; S->cut_above = (int)run; S->cut_ties = (int)c; }
+            run += c;
+          }
+        }
+      }
+      __syncthreads();
+      if (S->cut_count < WALK_CH - 1) {
+        th.bits = (unsigned long long)S->cut_count;
+        krem = L - S->cut_above;
+        ntied = S->cut_ties;
+        tie = ntied > krem;
+      } else {
+        auto occupied = [&](int) { return true; };
+        auto keyfn = [&](int i) { return (unsigned long long)tbl[slot_at(i)].count; };
+        th.bits = block_radix_select(nscan, L, keyfn, occupied, &S->P, &tie, &krem, &ntied);
+      }
+      __syncthreads();
       if (tie) {
         const unsigned long long tb = th.bits;
         auto idkey = [&](int i) { return (unsigned long long)(0x7fffffff - P.g.dense_of[word_label(tbl[slot_at(i)].key)]); };
-        auto tied = [&](int i) { const WalkSlot t = tbl[slot_at(i)]; return t.key != WALK_EMPTY && (unsigned long long)t.count == tb; };
+        auto tied = [&](int i) { return (unsigned long long)tbl[slot_at(i)].count == tb; };
         bool tie2;
         int krem2;
         const unsigned long long tid_key = block_radix_select(nscan, krem, idkey, tied, &S->P, &tie2, &krem2);
@@ -215,7 +275,6 @@ __global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
     for (int i = tid; i < nscan; i += THREADS) {
       const WalkSlot ts = tbl[slot_at(i)];
       const uint32_t wd = ts.key;
-      if (wd == WALK_EMPTY) continue;
       const unsigned long long cnt = ts.count;
       bool sel = cnt > th.bits;
       int label = -1;
@@ -232,8 +291,8 @@ __global__ void __launch_bounds__(THREADS) mc_walk_kernel(WalkParams P) {
     }
     for (int i = kept + tid; i < Lp; i += THREADS) out_ids[i] = KEY_EMPTY;
     __syncthreads();
-    if (GLOBAL)  // leave the table empty for the next source
-      for (int i = tid; i < n; i += THREADS) { const unsigned int h = glist[i]; tbl[h].key = WALK_EMPTY; tbl[h].count = 0u; }
+    // leave the table empty for the next source
+    for (int i = tid; i < n; i += THREADS) { const unsigned int h = slot_at(i); tbl[h].key = WALK_EMPTY; tbl[h].count = 0u; }
     publish_slot(P.peers, write_slot, (size_t)p * slot_bytes(Lp), slot_bytes(Lp), tid, THREADS);
     steps = (unsigned long long)block_reduce_sum_ll((long long)steps, S->P.red_a);
     if (tid == 0) {

@@ -905,6 +905,7 @@ static cudaError_t launch_walk_t(pprb200_session* s, const WalkParams& P, int gr
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(mc_walk_kernel<GLOBAL, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(mc_walk_kernel<GLOBAL, THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = smem;
   }
   mc_walk_kernel<GLOBAL, THREADS><<<grid, THREADS, smem, s->stream>>>(P);
@@ -963,18 +964,22 @@ static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t 
     // shared-memory table sized for the expected number of distinct visited nodes (<= hops + 1)
     const double len = damping >= 1.0 ? (double)MC_MAX_STEPS : std::min<double>((double)MC_MAX_STEPS, 1.0 / (1.0 - damping));
     const double expect = std::min<double>((double)s->n + 1.0, 1.0 + (double)W * len * 0.8);
-    unsigned int tcap = 1024;
-    while ((double)tcap * 0.75 < expect && tcap < 16384u) tcap <<= 1;
+    // capacities: powers of two and the 1.5x steps between them (the table is indexed by mulhi, not by a mask)
+    const unsigned int caps[] = {1024u, 1536u, 2048u, 3072u, 4096u, 6144u, 8192u, 12288u, 16384u};
+    unsigned int tcap = 16384u;
+    for (const unsigned int c : caps)
+      if ((double)c * 0.75 >= expect) { tcap = c; break; }
     int walk_threads = 256;  // measured on R-MAT-20, R=1000: 256 threads 19.8 G hops/s, 128 threads 12.3 G hops/s (fewer walks in flight)
     if (const char* e = getenv("PPRB200_WALK_THREADS")) walk_threads = atoi(e) == 256 ? 256 : 128;
     if (const char* e = getenv("PPRB200_WALK_TCAP")) {  // test hook: force the fallback path
-      unsigned int want = (unsigned int)std::max(1024, atoi(e));
-      tcap = 1024;
-      while (tcap < want && tcap < 16384u) tcap <<= 1;
+      const unsigned int want = (unsigned int)std::max(1024, atoi(e));
+      tcap = 16384u;
+      for (const unsigned int c : caps)
+        if (c >= want) { tcap = c; break; }
     }
     P.tcap = tcap; P.limit = tcap * 3 / 4 - 1;
     P.work_idx = 0; P.queue_in = nullptr; P.queue_in_idx = -1; P.queue_out = s->d_queue[0]; P.queue_out_idx = 0;
-    const size_t smem = ((sizeof(WalkShared) + 15) & ~(size_t)15) + (size_t)tcap * sizeof(WalkSlot);
+    const size_t smem = ((sizeof(WalkShared) + 15) & ~(size_t)15) + (size_t)tcap * (sizeof(WalkSlot) + sizeof(unsigned short));
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(walk_threads == 128 ? 16 : 8, (size_t)(227 * 1024) / (smem + 1024)));
     cudaError_t e = launch_walk<false>(s, P, std::max(1, std::min(s->M, s->sm_count * per_sm)), smem, walk_threads);
     if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "mc_walk launch failed: %s", cudaGetErrorString(e));
