@@ -575,7 +575,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 3 : 1)) merge_par_k
           fr->sa = fr->sb = make_double2(0.0, 0.0);
           if (j < tlen) {
             const uint32_t cc = s_col[j];
-            if (!(cc & COL_SINK) && lane < groups) load_frag_all(slot_of(cc), Lp, lane, fr);
+            if (!(cc & COL_SINK) && lane < groups) {
+              // pass 2 decides on the labels alone: the scores (2/3 of the bytes) are fetched only by lanes that hold a survivor
+              if (pass == 2) fr->id = __ldg(reinterpret_cast<const int4*>(slot_of(cc)) + lane);
+              else load_frag_all(slot_of(cc), Lp, lane, fr);
+            }
           }
         };
         BasketFrag f0, f1;
@@ -613,10 +617,13 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 3 : 1)) merge_par_k
               else {
                 fr.id = make_int4(-1, -1, -1, -1);
                 fr.sa = fr.sb = make_double2(0.0, 0.0);
-                if (g0 + lane < groups) load_frag_all(slot_of(c), Lp, g0 + lane, &fr);
+                if (g0 + lane < groups) {
+                  if (pass == 2) fr.id = __ldg(reinterpret_cast<const int4*>(slot_of(c)) + g0 + lane);
+                  else load_frag_all(slot_of(c), Lp, g0 + lane, &fr);
+                }
               }
               const int ids[4] = {fr.id.x, fr.id.y, fr.id.z, fr.id.w};
-              const double xs[4] = {fr.sa.x, fr.sa.y, fr.sb.x, fr.sb.y};
+              double xs[4] = {fr.sa.x, fr.sa.y, fr.sb.x, fr.sb.y};
               if (pass == 1) {
                 // lean pass: no queue, no votes -- every entry is one or two shared-memory atomics on the dense word, on the
                 // exact accumulator of an old-basket label, or on its sketch bucket
@@ -651,6 +658,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 3 : 1)) merge_par_k
                   merged += (k >= 0);
                 }
                 if (__any_sync(FULL, mine)) {
+                  if (mine) {
+                    const double2* sc = reinterpret_cast<const double2*>(slot_of(c) + (size_t)Lp * 4);
+                    const double2 sa = __ldg(sc + g0 + lane), sb = __ldg(sc + (Lp >> 2) + g0 + lane);
+                    xs[0] = sa.x; xs[1] = sa.y; xs[2] = sb.x; xs[3] = sb.y;
+                  }
 #pragma unroll
                   for (int e = 0; e < 4; e++) contribute(ids[e], (unsigned long long)__double2ll_rn(xs[e] * fscale));
                 }
