@@ -160,21 +160,12 @@ void host_indegree(const int32_t* col, int64_t e, int32_t n, uint32_t* indeg) {
   });
 }
 
-// Reference semantics (pprInternal.h:29-99): roots are taken in map-iteration order (= ascending dense id here) and go
-// to `first`; a popped node colours its unvisited successors and predecessors opposite to itself; the queue is FIFO.
-// Hence colour(v) = parity of the undirected BFS distance from the root of v's component (the smallest dense id in
-// it), whatever the visiting order inside a level (SURVEY.md 8-f2): the colouring below is level-synchronous, and the
-// levels of large components are expanded by all host threads. oracle/ppr_oracle.c keeps the literal FIFO version;
-// tests/test_host_logic.py compares the two.
-int find_partitions(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8_t* colour) {
-  if (n == 0) return PPRB200_OK;
+// CSR transpose: predecessor lists by ascending source id, multiplicity kept (= the order pprInternal.h:34-43 produces)
+void host_transpose(const int64_t* row_ptr, const int32_t* col, int32_t n, std::vector<int64_t>& prow, std::vector<int32_t>& pcol) {
   const int64_t e = row_ptr[n];
-  const bool timing = getenv("PPRB200_HOST_TIMING") != nullptr;
-  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  const double t_begin = now();
   // predecessor lists (CSR transpose); node ranges balanced by edge count, private cursors per range
-  std::vector<int64_t> prow((size_t)n + 1, 0);
-  std::vector<int32_t> pcol((size_t)std::max<int64_t>(e, 1));
+  prow.assign((size_t)n + 1, 0);
+  pcol.assign((size_t)std::max<int64_t>(e, 1), 0);
   {
     int parts = (int)std::min<int64_t>(host_threads(), (e + (1 << 16) - 1) / (1 << 16));
     while (parts > 1 && (int64_t)parts * n * 4 > (256ll << 20)) parts--;
@@ -220,6 +211,23 @@ int find_partitions(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8
       });
     }
   }
+}
+
+// Reference semantics (pprInternal.h:29-99): roots are taken in map-iteration order (= ascending dense id here) and go
+// to `first`; a popped node colours its unvisited successors and predecessors opposite to itself; the queue is FIFO.
+// Hence colour(v) = parity of the undirected BFS distance from the root of v's component (the smallest dense id in
+// it), whatever the visiting order inside a level (SURVEY.md 8-f2): the colouring below is level-synchronous, and the
+// levels of large components are expanded by all host threads. oracle/ppr_oracle.c keeps the literal FIFO version;
+// tests/test_host_logic.py compares the two.
+int find_partitions(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8_t* colour) {
+  if (n == 0) return PPRB200_OK;
+  const int64_t e = row_ptr[n];
+  const bool timing = getenv("PPRB200_HOST_TIMING") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
+  std::vector<int64_t> prow;
+  std::vector<int32_t> pcol;
+  host_transpose(row_ptr, col, n, prow, pcol);
   const double t_transposed = now();
   std::vector<uint8_t> seen((size_t)n, 0);
   std::vector<int32_t> frontier, next;

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "mc_walk.cuh"
+#include "ppr_exact.cuh"
 #include "merge_par.cuh"
 #include "ppr_internal.h"
 
@@ -1098,6 +1099,9 @@ static int session_fetch_impl(pprb200_session* s, int32_t* out_ids, double* out_
 
 static std::mutex g_api_mutex;  // one run at a time per process (SURVEY.md 8b re-entrancy)
 
+template <int BT>
+static void launch_exact_iter(const ExactParams& P, int grid, cudaStream_t st) { ppr_exact_iter_kernel<BT><<<grid, 256, 0, st>>>(P); }
+
 extern "C" {
 
 int pprb200_device_count(void) {
@@ -1223,6 +1227,124 @@ int pprb200_session_ipc_attach(pprb200_session* s, const void* all_handles) {
   }
   s->peers = pd;
   s->attached = true;
+  return PPRB200_OK;
+}
+
+// ---- quality evaluator yardstick: batched exact PPR (pprSingleSource.h:28-75) -----------------
+
+int pprb200_ppr_exact(const int64_t* row_ptr, const int32_t* col, int32_t n, const int32_t* sources, uint32_t n_sources,
+                      uint32_t iterations, double damping, double tolerance, double* out_scores, uint32_t* out_iterations,
+                      double* kernel_ms) {
+  // pprSingleSource.h:37-39, before the graph is touched
+  if (iterations == 0) return fail(PPRB200_ERR_PARAM, "iterations must be positive");
+  if (!(damping >= 0 && damping <= 1)) return fail(PPRB200_ERR_PARAM, "damping must be [0,1]");
+  int rc = validate_csr(row_ptr, col, n);
+  if (rc) return rc;
+  if (n_sources == 0) return PPRB200_OK;
+  if (!sources || !out_scores) return fail(PPRB200_ERR_PARAM, "NULL argument");
+  for (uint32_t i = 0; i < n_sources; i++)
+    if (sources[i] < 0 || sources[i] >= n) return fail(PPRB200_ERR_PARAM, "source node not part of the graph");
+  if ((rc = device_ok())) return rc;
+  std::lock_guard<std::mutex> lk(g_api_mutex);
+  pool_setup_once();
+  cudaStream_t st = nullptr;
+  g_alloc_stream = st;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+  std::vector<int64_t> prow;
+  std::vector<int32_t> pcol;
+  host_transpose(row_ptr, col, n, prow, pcol);
+  std::vector<double> factor((size_t)n, 0.0);
+  host_parallel_for(n, 1 << 15, [&](int, int64_t lo, int64_t hi) {
+    for (int64_t u = lo; u < hi; u++) {
+      const int64_t d = row_ptr[u + 1] - row_ptr[u];
+      if (d > 0) factor[(size_t)u] = damping / (double)(uint64_t)d;  // pprSingleSource.h:57
+    }
+  });
+  const int64_t E = row_ptr[n];
+  long long* d_prow = nullptr;
+  int* d_pcol = nullptr;
+  double* d_factor = nullptr;
+  double* d_buf[2] = {nullptr, nullptr};
+  int* d_src = nullptr;
+  int* d_active = nullptr;
+  int* d_parity = nullptr;
+  long long* d_diff = nullptr;
+  unsigned int* d_iters = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  auto cleanup = [&]() {
+    dev_free(d_prow); dev_free(d_pcol); dev_free(d_factor); dev_free(d_buf[0]); dev_free(d_buf[1]); dev_free(d_src);
+    dev_free(d_active); dev_free(d_parity); dev_free(d_diff); dev_free(d_iters);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  };
+  // sources advance in batches of up to 256 (8 scores per lane), bounded so that the two score arrays fit in 16 GB
+  const uint32_t by_mem = (uint32_t)std::max<uint64_t>(1, ((uint64_t)8 << 30) / ((uint64_t)std::max(n, 1) * 8));
+  const uint32_t batch_max = std::min<uint32_t>(256u, std::max<uint32_t>(1u, by_mem));
+  const uint32_t Bcap = std::min<uint32_t>(batch_max, n_sources);
+  if ((rc = dev_alloc(&d_prow, (size_t)n + 1)) || (rc = dev_alloc(&d_pcol, (size_t)std::max<int64_t>(E, 1))) ||
+      (rc = dev_alloc(&d_factor, (size_t)n)) || (rc = dev_alloc(&d_buf[0], (size_t)n * Bcap)) || (rc = dev_alloc(&d_buf[1], (size_t)n * Bcap)) ||
+      (rc = dev_alloc(&d_src, Bcap)) || (rc = dev_alloc(&d_active, Bcap)) || (rc = dev_alloc(&d_parity, 1)) ||
+      (rc = dev_alloc(&d_diff, Bcap)) || (rc = dev_alloc(&d_iters, Bcap))) {
+    cleanup();
+    return rc;
+  }
+  static_assert(sizeof(long long) == sizeof(int64_t), "row offsets");
+  cudaMemcpyAsync(d_prow, prow.data(), ((size_t)n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st);
+  if (E) cudaMemcpyAsync(d_pcol, pcol.data(), (size_t)E * sizeof(int), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_factor, factor.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st);
+  cudaEventCreate(&ev0);
+  cudaEventCreate(&ev1);
+  double total_ms = 0;
+  std::vector<double> stage;
+  std::vector<int> ones;
+  for (uint32_t b0 = 0; b0 < n_sources; b0 += Bcap) {
+    const int B = (int)std::min<uint32_t>(Bcap, n_sources - b0);
+    ones.assign((size_t)B, 1);
+    cudaMemsetAsync(d_buf[0], 0, (size_t)n * B * sizeof(double), st);
+    cudaMemsetAsync(d_parity, 0, sizeof(int), st);
+    cudaMemsetAsync(d_diff, 0, (size_t)B * sizeof(long long), st);
+    cudaMemsetAsync(d_iters, 0, (size_t)B * sizeof(unsigned int), st);
+    cudaMemcpyAsync(d_src, sources + b0, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_active, ones.data(), (size_t)B * sizeof(int), cudaMemcpyHostToDevice, st);
+    ExactParams P;
+    P.prow = d_prow; P.pcol = d_pcol; P.factor = d_factor; P.buf[0] = d_buf[0]; P.buf[1] = d_buf[1]; P.parity = d_parity;
+    P.source = d_src; P.active = d_active; P.diff = d_diff; P.iters = d_iters; P.n = n; P.B = B;
+    P.teleport = 1.0 - damping; P.tolerance = tolerance;
+    cudaEventRecord(ev0, st);
+    ppr_exact_init_kernel<<<(B + 255) / 256, 256, 0, st>>>(d_buf[0], d_src, B);
+    const int grid = std::max(1, std::min((n + 7) / 8, sms * 8));
+    const int bt = (B + 31) / 32;
+    for (uint32_t it = 0; it < iterations; it++) {
+      if (bt <= 1) launch_exact_iter<1>(P, grid, st);
+      else if (bt <= 2) launch_exact_iter<2>(P, grid, st);
+      else if (bt <= 4) launch_exact_iter<4>(P, grid, st);
+      else launch_exact_iter<8>(P, grid, st);
+      ppr_exact_step_kernel<<<1, 256, 0, st>>>(P);
+    }
+    cudaEventRecord(ev1, st);
+    int parity = 0;
+    cudaMemcpyAsync(&parity, d_parity, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cleanup(); return fail(PPRB200_ERR_CUDA, "exact PPR failed: %s", cudaGetErrorString(e)); }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    total_ms += ms;
+    // [n][B] on the device -> out_scores[source][n]
+    stage.resize((size_t)n * B);
+    cudaMemcpy(stage.data(), d_buf[parity], (size_t)n * B * sizeof(double), cudaMemcpyDeviceToHost);
+    host_parallel_for(B, 1, [&](int, int64_t lo, int64_t hi) {
+      for (int64_t b = lo; b < hi; b++) {
+        double* dst = out_scores + (size_t)(b0 + b) * (size_t)n;
+        for (int32_t v = 0; v < n; v++) dst[v] = stage[(size_t)v * B + (size_t)b];
+      }
+    });
+    if (out_iterations) cudaMemcpy(out_iterations + b0, d_iters, (size_t)B * sizeof(unsigned int), cudaMemcpyDeviceToHost);
+  }
+  if (kernel_ms) *kernel_ms = total_ms;
+  cleanup();
   return PPRB200_OK;
 }
 

@@ -142,6 +142,16 @@ int pprb200_shard_owner(const int64_t* row_ptr, const int32_t* col, int32_t n, c
 /* Kernels the last run enqueued on the session stream (bench.py's gpu_launches). */
 int pprb200_session_launches(pprb200_session* s, uint64_t* launches);
 
+/* Quality-evaluator yardstick: exact Personalized PageRank by power iteration for a batch of
+ * sources -- replaces ppr::pprInternal::pprSingleSource (/root/reference/include/internal/pprSingleSource.h:28-75)
+ * as include/benchmarkAlgorithm.h:91 calls it, once per sampled node. out_scores[i*n + v] = score of node v for
+ * sources[i] (0 for unreached nodes); out_iterations[i] (nullable) = iterations that source ran (it stops on its own
+ * once its norm-1 change drops below `tolerance`; negative = never); kernel_ms (nullable) = device time. */
+int pprb200_ppr_exact(const int64_t* row_ptr, const int32_t* col, int32_t n, const int32_t* sources, uint32_t n_sources,
+                      uint32_t iterations, double damping, double tolerance, double* out_scores, uint32_t* out_iterations,
+                      double* kernel_ms);
+
+
 /* ---- synthetic workloads of BASELINE.json (host only; used by bench.py and the tests) --------------- */
 
 /* R-MAT (a,b,c,1-a-b-c), 2^scale nodes, edge_factor*2^scale directed edges, duplicates and self-loops

@@ -24,6 +24,7 @@
 #include <grankMulti.h>        // /root/reference/header-only/grankMulti.h
 #include <mccompletepathv2.h>  // /root/reference/include/mccompletepathv2.h
 #include <pprSingleSource.h>   // /root/reference/include/internal/pprSingleSource.h
+#include <kendall.h>           // /root/reference/include/internal/kendall.h
 
 typedef std::unordered_map<int, std::vector<int>> graph_t;
 typedef std::unordered_map<int, std::unordered_map<int, double>> result_t;
@@ -151,3 +152,12 @@ double ref_norm1(const int32_t* ids1, const double* s1, int32_t c1, const int32_
 }
 
 }  // extern "C"
+
+// kendall.h:22-180 and pprInternal.h:174-186 (the quality evaluator's two statistics)
+extern "C" double ref_kendall(const double* x, const double* y, int32_t n) {
+  return kendallCorrelation(std::vector<double>(x, x + n), std::vector<double>(y, y + n));
+}
+
+extern "C" double ref_jaccard(const int32_t* a, int32_t na, const int32_t* b, int32_t nb) {
+  return ppr::pprInternal::jaccard<int>(std::unordered_set<int>(a, a + na), std::unordered_set<int>(b, b + nb));
+}

@@ -180,3 +180,19 @@ def baskets_to_keyspace(res, order):
         cnt[k] = c
     ids, sc = _sorted_rows(ids, sc, cnt)
     return Result(ids, sc, cnt)
+
+
+def ref_kendall(x, y):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    f = ref().ref_kendall
+    f.restype = C.c_double
+    return float(f(P(x), P(y), C.c_int32(len(x))))
+
+
+def ref_jaccard(a, b):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    b = np.ascontiguousarray(b, dtype=np.int32)
+    f = ref().ref_jaccard
+    f.restype = C.c_double
+    return float(f(P(a), C.c_int32(len(a)), P(b), C.c_int32(len(b))))

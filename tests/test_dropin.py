@@ -102,3 +102,25 @@ def test_flat_result_view_holds_what_the_maps_hold():
     """SURVEY.md 8-f1: ppr::b200::grankFlat / mccompletepathv2Flat (no n*K hash inserts) == the reference-typed maps."""
     r = run(ROOT / "tests" / "cpp" / "flat_check_b200")
     assert r.returncode == 0 and "flat_check OK" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_benchmark_algorithm_dropin_reports_the_reference_statistics():
+    """SURVEY.md 8-f3: tests/cpp/eval_check.cc (ppr::benchmarkAlgorithm over every node, so the random sampling drops
+    out) built against our headers vs the golden output of the build against the unmodified reference headers. The
+    exact top-K behind Jaccard is cut at arbitrary ties in the reference (keepTop), hence the small tolerances."""
+    r = run(ROOT / "tests" / "cpp" / "eval_check_b200")
+    assert r.returncode == 0, r.stdout + r.stderr
+
+    def stats(text):
+        return {ln.split(" = ")[0]: float(ln.split(" = ")[1]) for ln in text.strip().splitlines()}
+    ours, want = stats(r.stdout), stats((GOLDEN / "eval_check.txt").read_text())
+    assert set(ours) == set(want)
+    assert ours["no samples"] == want["no samples"] == -1.0
+    assert ours["average map size"] == want["average map size"]
+    for k, tol in (("jaccard average", 0.01), ("kendall average", 0.01), ("jaccard min", 0.1), ("kendall min", 0.1)):
+        assert abs(ours[k] - want[k]) <= tol, (k, ours[k], want[k])
+    ref_bin = ROOT / "oracle" / "_ref" / "eval_check_ref"
+    if ref_bin.exists():
+        q = run(ref_bin)
+        assert q.returncode == 0 and stats(q.stdout)["average map size"] == ours["average map size"]
