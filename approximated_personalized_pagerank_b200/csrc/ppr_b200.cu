@@ -654,12 +654,12 @@ static int enqueue_cascade(pprb200_session* s, MergeParams P, int range_begin, i
   const int Lp = roundup4(L);
   P.Lp = Lp;
   P.L = L;
-  const int caps[3] = {1024, 4096, 16384};
-  const int warps[3] = {14, 3, 1};
+  const int caps[4] = {1024, 2048, 4096, 16384};
+  const int warps[4] = {14, 7, 3, 1};
   bool have_source = false;  // false: next stage reads the range; true: reads queue `qsrc`
   int qsrc = -1;
   int work_idx = 0;
-  for (int i = 0; i < 3; i++) {
+  for (int i = 0; i < 4; i++) {
     const int limit = stage_limit(caps[i], Lp);
     if (limit < 8) continue;
     MergeParams Q = P;
@@ -673,7 +673,8 @@ static int enqueue_cascade(pprb200_session* s, MergeParams P, int range_begin, i
     const size_t smem = (size_t)warps[i] * ((size_t)caps[i] * 14 + 1040);
     cudaError_t e;
     if (i == 0) e = launch_stage<1024, 14, unsigned short>(s, Q, s->sm_count, smem, nullptr, 0, 0);
-    else if (i == 1) e = launch_stage<4096, 3, unsigned short>(s, Q, s->sm_count, smem, nullptr, 0, 0);
+    else if (i == 1) e = launch_stage<2048, 7, unsigned short>(s, Q, s->sm_count, smem, nullptr, 0, 0);
+    else if (i == 2) e = launch_stage<4096, 3, unsigned short>(s, Q, s->sm_count, smem, nullptr, 0, 0);
     else e = launch_stage<16384, 1, unsigned short>(s, Q, s->sm_count, smem, nullptr, 0, 0);
     if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge stage %d launch failed: %s", i, cudaGetErrorString(e));
     have_source = true;
@@ -752,7 +753,7 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
     P.item_begin = s->d_item_off + b;
     P.item_len = s->d_item_len + b;
     P.n_items = e - b;
-    P.work_idx = 4 + cls;
+    P.work_idx = 6 + cls;  // (0..4: the exact-order cascade)
     P.pool = s->d_pool + s->pool_off[cls];
     P.capmax = s->tbl_cap[cls];
     P.tbl_bytes = (size_t)s->tbl_cap[cls] * (sizeof(GSlot) + sizeof(unsigned int) + 4 + 2);
