@@ -265,8 +265,4 @@ struct Threshold {
   int id_max;
 };
 
-__device__ __forceinline__ bool is_selected(const Threshold& t, unsigned long long bits, int id) {
-  return bits > t.bits || (bits == t.bits && id <= t.id_max);
-}
-
 }  // namespace pprb200

@@ -64,24 +64,6 @@ struct ParShared {
 
 // CTA-wide reductions: warp shuffles, one shared-memory word per warp, then every warp folds the (<= 32) partial
 // results with shuffles again -- no serial loop over the warps. All threads must call; `scratch` holds >= 32 words.
-__device__ __forceinline__ unsigned long long block_reduce_min_ull(unsigned long long v, unsigned long long* scratch) {
-  v = warp_min_ull(v);
-  const int nw = (int)(blockDim.x >> 5);
-  if (lane_id() == 0) scratch[threadIdx.x >> 5] = v;
-  __syncthreads();
-  unsigned long long r = warp_min_ull(lane_id() < nw ? scratch[lane_id()] : ~0ull);
-  __syncthreads();
-  return r;
-}
-__device__ __forceinline__ unsigned long long block_reduce_max_ull(unsigned long long v, unsigned long long* scratch) {
-  v = warp_max_ull(v);
-  const int nw = (int)(blockDim.x >> 5);
-  if (lane_id() == 0) scratch[threadIdx.x >> 5] = v;
-  __syncthreads();
-  unsigned long long r = warp_max_ull(lane_id() < nw ? scratch[lane_id()] : 0ull);
-  __syncthreads();
-  return r;
-}
 __device__ __forceinline__ long long block_reduce_sum_ll(long long v, unsigned long long* scratch) {
   v = warp_sum_ll(v);
   const int nw = (int)(blockDim.x >> 5);

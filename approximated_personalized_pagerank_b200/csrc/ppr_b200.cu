@@ -651,7 +651,7 @@ static cudaError_t launch_stage(pprb200_session* s, const MergeParams& P, int gr
   return cudaGetLastError();
 }
 
-// Enqueue the table-size cascade for one colour (or, MC, for everything): 1024 -> 4096 -> 16384 -> global.
+// Enqueue the table-size cascade for one colour (or, MC, for everything): 1024 -> 2048 -> 4096 -> 16384 -> global.
 static int enqueue_cascade(pprb200_session* s, MergeParams P, int range_begin, int range_end, int L) {
   const int Lp = roundup4(L);
   P.Lp = Lp;
