@@ -2,6 +2,8 @@
 the C-ABI loads and exports every symbol of include/pprb200.h, parameter checks, findPartitions, generators."""
 import ctypes as C
 import io
+import sys
+from pathlib import Path
 import contextlib
 
 import numpy as np
@@ -11,6 +13,8 @@ import oracle_bindings as ob
 import approximated_personalized_pagerank_b200 as ppr
 from approximated_personalized_pagerank_b200 import _lib, graphs as G
 from conftest import golden_cases, load_golden, requires_ref
+
+ROOT = Path(__file__).resolve().parent.parent
 
 
 def test_library_exports_every_declared_symbol():
@@ -113,6 +117,54 @@ def test_find_partitions_matches_live_reference_on_rmat():
     g = G.rmat(11)
     gd, order = ob.to_reference_space(g)
     assert (ppr.find_partitions_csr(gd) == ob.ref_find_partitions(g)[order]).all()
+
+
+def test_parallel_colouring_matches_the_fifo_oracle_on_large_frontiers():
+    """The library colours level-synchronously on all host threads (host_graph.cc); the oracle keeps the reference's literal
+    FIFO queue (pprInternal.h:54-99). Large frontiers (R-MAT hubs, BA), long chains (ring) and many components."""
+    cases = [G.rmat(15), G.barabasi_albert(50000, 4), G.ring(30000)]
+    rng = np.random.default_rng(11)
+    n = 60000
+    cases.append(G.from_edges(n, rng.integers(0, n, 45000), rng.integers(0, n, 45000)))  # thousands of small components
+    for g in cases:
+        assert (ppr.find_partitions_csr(g) == ob.oracle_find_partitions(g)).all()
+
+
+def test_host_thread_count_does_not_change_the_colouring():
+    code = ("import sys; sys.path.insert(0, %r); import numpy as np, approximated_personalized_pagerank_b200 as ppr;"
+            "from approximated_personalized_pagerank_b200 import graphs as G;"
+            "c = ppr.find_partitions_csr(G.rmat(14)); sys.stdout.write(str(int(np.dot(c.astype(np.int64), np.arange(c.size) %% 1009))))" % str(ROOT))
+    import os, subprocess
+    outs = set()
+    for t in ("1", "3", "16"):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, PPRB200_HOST_THREADS=t))
+        assert r.returncode == 0, r.stderr
+        outs.add(r.stdout.strip())
+    assert len(outs) == 1, outs
+
+
+def test_host_pool_serialises_concurrent_callers():
+    import threading
+    g = G.rmat(13)
+    want = ob.oracle_find_partitions(g)
+    bad = []
+
+    def work():
+        for _ in range(5):
+            if not (ppr.find_partitions_csr(g) == want).all():
+                bad.append(1)
+    ts = [threading.Thread(target=work) for _ in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not bad
+
+
+def test_malformed_successor_is_reported_with_its_edge():
+    g = G.from_edges(5, [0, 1, 2], [1, 2, 3])
+    col = g.col.copy()
+    col[1] = 7
+    with pytest.raises(_lib.PprB200Error, match="successor 7 at edge 1 is not a node"):
+        ppr.find_partitions_csr(G.CSRGraph(g.row_ptr, col))
 
 
 def test_rmat_generator_matches_numpy_restatement():
