@@ -1103,7 +1103,10 @@ static int session_fetch_impl(pprb200_session* s, int32_t* out_ids, double* out_
 static std::mutex g_api_mutex;  // one run at a time per process (SURVEY.md 8b re-entrancy)
 
 template <int BT>
-static void launch_exact_iter(const ExactParams& P, int grid, cudaStream_t st) { ppr_exact_iter_kernel<BT><<<grid, 256, 0, st>>>(P); }
+static void launch_exact_iter(const ExactParams& P, int grid, int sms, cudaStream_t st) {
+  ppr_exact_iter_kernel<BT><<<grid, 256, 0, st>>>(P);
+  if (P.n_heavy > 0) ppr_exact_heavy_kernel<BT><<<std::min(P.n_heavy, sms * 4), 256, 0, st>>>(P);
+}
 
 extern "C" {
 
@@ -1267,6 +1270,12 @@ int pprb200_ppr_exact(const int64_t* row_ptr, const int32_t* col, int32_t n, con
     }
   });
   const int64_t E = row_ptr[n];
+  std::vector<int> heavy;  // nodes whose predecessor list gets a CTA of its own
+  int heavy_threshold = EXACT_HEAVY;
+  if (const char* e = getenv("PPRB200_EXACT_HEAVY")) heavy_threshold = std::max(32, atoi(e));
+  for (int32_t v = 0; v < n; v++)
+    if (prow[(size_t)v + 1] - prow[(size_t)v] > heavy_threshold) heavy.push_back(v);
+  int* d_heavy = nullptr;
   long long* d_prow = nullptr;
   int* d_pcol = nullptr;
   double* d_factor = nullptr;
@@ -1279,7 +1288,7 @@ int pprb200_ppr_exact(const int64_t* row_ptr, const int32_t* col, int32_t n, con
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   auto cleanup = [&]() {
     dev_free(d_prow); dev_free(d_pcol); dev_free(d_factor); dev_free(d_buf[0]); dev_free(d_buf[1]); dev_free(d_src);
-    dev_free(d_active); dev_free(d_parity); dev_free(d_diff); dev_free(d_iters);
+    dev_free(d_active); dev_free(d_parity); dev_free(d_diff); dev_free(d_iters); dev_free(d_heavy);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
   };
@@ -1290,10 +1299,11 @@ int pprb200_ppr_exact(const int64_t* row_ptr, const int32_t* col, int32_t n, con
   if ((rc = dev_alloc(&d_prow, (size_t)n + 1)) || (rc = dev_alloc(&d_pcol, (size_t)std::max<int64_t>(E, 1))) ||
       (rc = dev_alloc(&d_factor, (size_t)n)) || (rc = dev_alloc(&d_buf[0], (size_t)n * Bcap)) || (rc = dev_alloc(&d_buf[1], (size_t)n * Bcap)) ||
       (rc = dev_alloc(&d_src, Bcap)) || (rc = dev_alloc(&d_active, Bcap)) || (rc = dev_alloc(&d_parity, 1)) ||
-      (rc = dev_alloc(&d_diff, Bcap)) || (rc = dev_alloc(&d_iters, Bcap))) {
+      (rc = dev_alloc(&d_diff, Bcap)) || (rc = dev_alloc(&d_iters, Bcap)) || (rc = dev_alloc(&d_heavy, heavy.size()))) {
     cleanup();
     return rc;
   }
+  if (!heavy.empty()) cudaMemcpyAsync(d_heavy, heavy.data(), heavy.size() * sizeof(int), cudaMemcpyHostToDevice, st);
   static_assert(sizeof(long long) == sizeof(int64_t), "row offsets");
   cudaMemcpyAsync(d_prow, prow.data(), ((size_t)n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st);
   if (E) cudaMemcpyAsync(d_pcol, pcol.data(), (size_t)E * sizeof(int), cudaMemcpyHostToDevice, st);
@@ -1315,16 +1325,17 @@ int pprb200_ppr_exact(const int64_t* row_ptr, const int32_t* col, int32_t n, con
     ExactParams P;
     P.prow = d_prow; P.pcol = d_pcol; P.factor = d_factor; P.buf[0] = d_buf[0]; P.buf[1] = d_buf[1]; P.parity = d_parity;
     P.source = d_src; P.active = d_active; P.diff = d_diff; P.iters = d_iters; P.n = n; P.B = B;
+    P.heavy = d_heavy; P.n_heavy = (int)heavy.size(); P.heavy_threshold = heavy_threshold;
     P.teleport = 1.0 - damping; P.tolerance = tolerance;
     cudaEventRecord(ev0, st);
     ppr_exact_init_kernel<<<(B + 255) / 256, 256, 0, st>>>(d_buf[0], d_src, B);
     const int grid = std::max(1, std::min((n + 7) / 8, sms * 8));
     const int bt = (B + 31) / 32;
     for (uint32_t it = 0; it < iterations; it++) {
-      if (bt <= 1) launch_exact_iter<1>(P, grid, st);
-      else if (bt <= 2) launch_exact_iter<2>(P, grid, st);
-      else if (bt <= 4) launch_exact_iter<4>(P, grid, st);
-      else launch_exact_iter<8>(P, grid, st);
+      if (bt <= 1) launch_exact_iter<1>(P, grid, sms, st);
+      else if (bt <= 2) launch_exact_iter<2>(P, grid, sms, st);
+      else if (bt <= 4) launch_exact_iter<4>(P, grid, sms, st);
+      else launch_exact_iter<8>(P, grid, sms, st);
       ppr_exact_step_kernel<<<1, 256, 0, st>>>(P);
     }
     cudaEventRecord(ev1, st);
