@@ -757,7 +757,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 3 : 1)) merge_par_k
     // exact as long as at least L candidates remain (the L-th largest of a subset bounds the cut from below);
     // otherwise theta is relaxed and the compaction repeated.
     double theta0 = 0.0;
-    if (!init_mode && M.do_norm) {
+    if (!init_mode) {  // (MC combine rounds too: the node's previous basket is on the same score scale)
       const unsigned char* old = M.buf[write_slot ^ 1] + (size_t)p * slot_bytes(Lp);
       const int* oid = reinterpret_cast<const int*>(old);
       const double* osc = reinterpret_cast<const double*>(old + (size_t)Lp * 4);
