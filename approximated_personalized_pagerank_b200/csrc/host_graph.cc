@@ -221,7 +221,6 @@ void host_transpose(const int64_t* row_ptr, const int32_t* col, int32_t n, std::
 // tests/test_host_logic.py compares the two.
 int find_partitions(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8_t* colour) {
   if (n == 0) return PPRB200_OK;
-  const int64_t e = row_ptr[n];
   const bool timing = getenv("PPRB200_HOST_TIMING") != nullptr;
   auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_begin = now();

@@ -3,7 +3,7 @@
 // quality statistics of benchmarkAlgorithm. Because it only uses the reference's public API it also builds against the
 // reference's own include directories.
 //
-//   g++ -std=c++11 -O2 -I approximated_personalized_pagerank_b200/cpp/include -I include examples/demo_main.cc \
+//   g++ -std=c++11 -O2 -I approximated_personalized_pagerank_b200/cpp/include -I include examples/demo_main.cc
 //       -L approximated_personalized_pagerank_b200 -lppr_b200 -Wl,-rpath,$PWD/approximated_personalized_pagerank_b200 -lpthread -o demo
 //   ./demo edges.csv
 #include <chrono>
