@@ -160,21 +160,41 @@ void host_indegree(const int32_t* col, int64_t e, int32_t n, uint32_t* indeg) {
   });
 }
 
-// CSR transpose: predecessor lists by ascending source id, multiplicity kept (= the order pprInternal.h:34-43 produces)
-void host_transpose(const int64_t* row_ptr, const int32_t* col, int32_t n, std::vector<int64_t>& prow, std::vector<int32_t>& pcol) {
+// CSR transpose: predecessor lists by ascending source id, multiplicity kept (= the order pprInternal.h:34-43 produces);
+// edges whose source has skip_source[u] != 0 are left out (nullptr: none)
+void host_transpose(const int64_t* row_ptr, const int32_t* col, int32_t n, std::vector<int64_t>& prow, std::vector<int32_t>& pcol,
+                    const uint8_t* skip_source) {
   const int64_t e = row_ptr[n];
+  auto skipped = [&](int32_t u) { return skip_source != nullptr && skip_source[(size_t)u] != 0; };
   // predecessor lists (CSR transpose); node ranges balanced by edge count, private cursors per range
   prow.assign((size_t)n + 1, 0);
-  pcol.assign((size_t)std::max<int64_t>(e, 1), 0);
   {
-    int parts = (int)std::min<int64_t>(host_threads(), (e + (1 << 16) - 1) / (1 << 16));
+    int64_t e_eff = e;  // edges that are actually transposed
+    if (skip_source != nullptr) {
+      std::vector<int64_t> part_sum((size_t)host_threads(), 0);
+      host_parallel_for(n, 1 << 16, [&](int t, int64_t lo, int64_t hi) {
+        int64_t acc = 0;
+        for (int64_t u = lo; u < hi; u++)
+          if (!skip_source[(size_t)u]) acc += row_ptr[u + 1] - row_ptr[u];
+        part_sum[(size_t)t] = acc;
+      });
+      e_eff = 0;
+      for (const int64_t x : part_sum) e_eff += x;
+    }
+    // private histograms cost parts * n words: only worth it when there are many more edges than nodes per thread
+    pcol.resize((size_t)std::max<int64_t>(e_eff, 1));
+    int parts = (int)std::min<int64_t>(host_threads(), (e_eff + (1 << 16) - 1) / (1 << 16));
+    if (e_eff < (int64_t)n) parts = 1;
     while (parts > 1 && (int64_t)parts * n * 4 > (256ll << 20)) parts--;
     if (parts <= 1) {
-      for (int64_t i = 0; i < e; i++) prow[(size_t)col[i] + 1]++;
+      for (int32_t u = 0; u < n; u++)
+        if (!skipped(u))
+          for (int64_t i = row_ptr[u]; i < row_ptr[u + 1]; i++) prow[(size_t)col[i] + 1]++;
       for (int32_t v = 0; v < n; v++) prow[(size_t)v + 1] += prow[v];
       std::vector<int64_t> cursor(prow.begin(), prow.end() - 1);
       for (int32_t u = 0; u < n; u++)
-        for (int64_t i = row_ptr[u]; i < row_ptr[u + 1]; i++) pcol[(size_t)cursor[col[i]]++] = u;
+        if (!skipped(u))
+          for (int64_t i = row_ptr[u]; i < row_ptr[u + 1]; i++) pcol[(size_t)cursor[col[i]]++] = u;
     } else {
       std::vector<int32_t> cut((size_t)parts + 1, 0);  // node ranges with ~e/parts edges each
       for (int t = 1; t < parts; t++)
@@ -185,7 +205,9 @@ void host_transpose(const int64_t* row_ptr, const int32_t* col, int32_t n, std::
       host_parallel(parts, [&](int t) {
         h[(size_t)t].assign((size_t)n, 0u);
         uint32_t* mine = h[(size_t)t].data();
-        for (int64_t i = row_ptr[cut[(size_t)t]], hi = row_ptr[cut[(size_t)t + 1]]; i < hi; i++) mine[(size_t)col[i]]++;
+        for (int32_t u = cut[(size_t)t]; u < cut[(size_t)t + 1]; u++)
+          if (!skipped(u))
+            for (int64_t i = row_ptr[u]; i < row_ptr[u + 1]; i++) mine[(size_t)col[i]]++;
       });
       host_parallel_for(n, 1 << 14, [&](int, int64_t lo, int64_t hi) {
         for (int64_t v = lo; v < hi; v++) {
@@ -204,10 +226,11 @@ void host_transpose(const int64_t* row_ptr, const int32_t* col, int32_t n, std::
       host_parallel(parts, [&](int t) {
         uint32_t* mine = h[(size_t)t].data();
         for (int32_t u = cut[(size_t)t]; u < cut[(size_t)t + 1]; u++)
-          for (int64_t i = row_ptr[u]; i < row_ptr[u + 1]; i++) {
-            const int32_t s = col[i];
-            pcol[(size_t)(prow[(size_t)s] + mine[(size_t)s]++)] = u;
-          }
+          if (!skipped(u))
+            for (int64_t i = row_ptr[u]; i < row_ptr[u + 1]; i++) {
+              const int32_t s = col[i];
+              pcol[(size_t)(prow[(size_t)s] + mine[(size_t)s]++)] = u;
+            }
       });
     }
   }
@@ -224,28 +247,111 @@ int find_partitions(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8
   const bool timing = getenv("PPRB200_HOST_TIMING") != nullptr;
   auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_begin = now();
+  const int64_t e = row_ptr[n];
+  const int T = host_threads();
+  std::vector<uint8_t> seen((size_t)n, 0);  // phase A: 0 unseen, 1 seen, 2 current frontier, 3 next frontier
+  std::vector<int32_t> frontier, next;
+  std::vector<std::vector<int32_t>> local((size_t)T);
+  int32_t first_root = 0;
+  uint8_t other = 1;
+
+  // ---- phase A: the first non-trivial component WITHOUT predecessor lists -------------------------------------------
+  // On power-law graphs one component holds nearly every edge, and building the transpose (random scatter of E entries)
+  // costs several times more than the BFS itself. In-edges are followed bottom-up instead: an unseen node whose successor
+  // is in the current frontier is a predecessor of the frontier, hence in the next level. Each level streams the out-edges
+  // of the still-unseen nodes (parallel over node ranges, no atomics: a thread writes only its own nodes). The scanned edges
+  // are budgeted at 4 E; a component that needs more levels than that (a long chain) continues in phase B.
+  double t_a = t_begin;
+  const bool phase_a = e >= (1 << 17);
+  if (phase_a) {
+    if (row_ptr[1] == row_ptr[0]) {  // node 0 has no out-edges: in-degrees tell isolated roots from sink roots
+      std::vector<uint32_t> indeg((size_t)n);
+      host_indegree(col, e, n, indeg.data());
+      while (first_root < n && row_ptr[first_root + 1] == row_ptr[first_root] && indeg[(size_t)first_root] == 0) {
+        seen[(size_t)first_root] = 1;  // isolated nodes are components of their own (pprInternal.h:58-64: root -> first)
+        colour[first_root++] = 0;
+      }
+    }
+    if (first_root < n) {
+      seen[(size_t)first_root] = 2;
+      colour[first_root] = 0;
+      frontier.assign(1, first_root);
+      long long budget = 4 * (long long)e;
+      std::vector<long long> scanned((size_t)T, 0);
+      while (!frontier.empty() && budget > 0) {
+        const int64_t fs = (int64_t)frontier.size();
+        const int fparts = (int)std::max<int64_t>(1, std::min<int64_t>(T, (fs + 511) / 512));
+        for (int t = 0; t < T; t++) local[(size_t)t].clear();
+        // top-down over the out-edges of the frontier
+        host_parallel(fparts, [&](int t) {
+          std::vector<int32_t>& out = local[(size_t)t];
+          for (int64_t k = fs * t / fparts, hi = fs * (t + 1) / fparts; k < hi; k++) {
+            const int32_t x = frontier[(size_t)k];
+            for (int64_t i = row_ptr[x]; i < row_ptr[x + 1]; i++) {
+              const int32_t sx = col[i];
+              if (__atomic_load_n(&seen[(size_t)sx], __ATOMIC_RELAXED) != 0) continue;
+              if (__atomic_exchange_n(&seen[(size_t)sx], (uint8_t)3, __ATOMIC_RELAXED) != 0) continue;
+              colour[sx] = other;
+              out.push_back(sx);
+            }
+          }
+        });
+        // bottom-up: unseen nodes with a successor in the current frontier
+        const int nparts = (int)std::max<int64_t>(1, std::min<int64_t>(T, ((int64_t)n + 4095) / 4096));
+        host_parallel(nparts, [&](int t) {
+          std::vector<int32_t>& out = local[(size_t)t];
+          long long cnt = 0;
+          for (int64_t v = (int64_t)n * t / nparts, hi = (int64_t)n * (t + 1) / nparts; v < hi; v++) {
+            if (seen[(size_t)v] != 0) continue;
+            for (int64_t i = row_ptr[v]; i < row_ptr[v + 1]; i++) {
+              cnt++;
+              if (seen[(size_t)col[i]] == 2) {
+                seen[(size_t)v] = 3;
+                colour[v] = other;
+                out.push_back((int32_t)v);
+                break;
+              }
+            }
+          }
+          scanned[(size_t)t] = cnt;
+        });
+        for (int t = 0; t < nparts; t++) budget -= scanned[(size_t)t];
+        for (const int32_t x : frontier) seen[(size_t)x] = 1;
+        next.clear();
+        for (int t = 0; t < T; t++) next.insert(next.end(), local[(size_t)t].begin(), local[(size_t)t].end());
+        for (const int32_t x : next) seen[(size_t)x] = 2;
+        frontier.swap(next);
+        other ^= 1u;
+      }
+      for (const int32_t x : frontier) seen[(size_t)x] = 1;  // (budget ran out mid-component: phase B goes on from this frontier)
+      first_root++;
+    }
+    t_a = now();
+  }
+
+  // ---- phase B: whatever is left, with predecessor lists restricted to edges that leave unseen nodes ------------------
+  // (an unseen node has only unseen predecessors, or predecessors in the frontier phase A handed over)
+  // (an unseen node that has in-edges has them from unseen nodes, which then have out-edges: looking at out-degrees is enough)
+  bool work_left = !frontier.empty() || !phase_a;
+  for (int32_t v = first_root; v < n && !work_left; v++) work_left = !seen[(size_t)v] && row_ptr[v + 1] > row_ptr[v];
+  if (!work_left) {
+    for (int32_t v = first_root; v < n; v++)
+      if (!seen[(size_t)v]) colour[v] = 0;  // isolated nodes
+    if (timing) fprintf(stderr, "[pprb200] find_partitions: transpose-free bfs %.2f ms (%d host threads)\n", now() - t_begin, T);
+    return PPRB200_OK;
+  }
   std::vector<int64_t> prow;
   std::vector<int32_t> pcol;
-  host_transpose(row_ptr, col, n, prow, pcol);
+  host_transpose(row_ptr, col, n, prow, pcol, phase_a ? seen.data() : nullptr);
   const double t_transposed = now();
-  std::vector<uint8_t> seen((size_t)n, 0);
-  std::vector<int32_t> frontier, next;
-  const int T = host_threads();
-  std::vector<std::vector<int32_t>> local((size_t)T);
-  for (int32_t root = 0; root < n; root++) {
-    if (seen[(size_t)root]) continue;
-    seen[(size_t)root] = 1;
-    colour[root] = 0;
-    if (row_ptr[root + 1] == row_ptr[root] && prow[(size_t)root + 1] == prow[(size_t)root]) continue;  // isolated node
-    frontier.assign(1, root);
-    uint8_t other = 1;
+  auto run_component = [&]() {  // level-synchronous BFS from `frontier`; the next level gets colour `other`
     while (!frontier.empty()) {
       next.clear();
       if (frontier.size() < 2048 || T == 1) {
         for (const int32_t x : frontier) {
           for (int64_t i = row_ptr[x]; i < row_ptr[x + 1]; i++) {
-            const int32_t s = col[i];
-            if (!seen[(size_t)s]) { seen[(size_t)s] = 1; colour[s] = other; next.push_back(s); }
+            const int32_t sx = col[i];
+            if (!seen[(size_t)sx]) { seen[(size_t)sx] = 1; colour[sx] = other; next.push_back(sx); }
           }
           for (int64_t i = prow[(size_t)x]; i < prow[(size_t)x + 1]; i++) {
             const int32_t p = pcol[(size_t)i];
@@ -258,11 +364,11 @@ int find_partitions(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8
         host_parallel(parts, [&](int t) {
           std::vector<int32_t>& out = local[(size_t)t];
           out.clear();
-          auto visit = [&](int32_t s) {
-            if (__atomic_load_n(&seen[(size_t)s], __ATOMIC_RELAXED)) return;
-            if (__atomic_exchange_n(&seen[(size_t)s], (uint8_t)1, __ATOMIC_RELAXED)) return;
-            colour[s] = other;
-            out.push_back(s);
+          auto visit = [&](int32_t sx) {
+            if (__atomic_load_n(&seen[(size_t)sx], __ATOMIC_RELAXED)) return;
+            if (__atomic_exchange_n(&seen[(size_t)sx], (uint8_t)1, __ATOMIC_RELAXED)) return;
+            colour[sx] = other;
+            out.push_back(sx);
           };
           for (int64_t k = fs * t / parts, hi = fs * (t + 1) / parts; k < hi; k++) {
             const int32_t x = frontier[(size_t)k];
@@ -275,8 +381,20 @@ int find_partitions(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8
       frontier.swap(next);
       other ^= 1u;
     }
+  };
+  run_component();  // the component phase A handed over, if any
+  for (int32_t root = first_root; root < n; root++) {
+    if (seen[(size_t)root]) continue;
+    seen[(size_t)root] = 1;
+    colour[root] = 0;
+    if (row_ptr[root + 1] == row_ptr[root] && prow[(size_t)root + 1] == prow[(size_t)root]) continue;  // isolated node
+    frontier.assign(1, root);
+    other = 1;
+    run_component();
   }
-  if (timing) fprintf(stderr, "[pprb200] find_partitions: transpose %.2f ms, bfs %.2f ms (%d host threads)\n", t_transposed - t_begin, now() - t_transposed, host_threads());
+  if (timing)
+    fprintf(stderr, "[pprb200] find_partitions: transpose-free bfs %.2f ms, restricted transpose %.2f ms, bfs %.2f ms (%d host threads)\n",
+            t_a - t_begin, t_transposed - t_a, now() - t_transposed, T);
   return PPRB200_OK;
 }
 

@@ -24,8 +24,10 @@ int host_threads();
 void host_parallel(int parts, const std::function<void(int)>& fn);
 // splits [0, n) into `parts` ranges and runs fn(part, lo, hi); runs inline when n is small or parts == 1
 void host_parallel_for(int64_t n, int64_t grain, const std::function<void(int, int64_t, int64_t)>& fn);
-// CSR transpose (predecessor lists by ascending source id, multiplicity kept), parallel
-void host_transpose(const int64_t* row_ptr, const int32_t* col, int32_t n, std::vector<int64_t>& prow, std::vector<int32_t>& pcol);
+// CSR transpose (predecessor lists by ascending source id, multiplicity kept), parallel; edges whose source has
+// skip_source[u] != 0 are left out
+void host_transpose(const int64_t* row_ptr, const int32_t* col, int32_t n, std::vector<int64_t>& prow, std::vector<int32_t>& pcol,
+                    const uint8_t* skip_source = nullptr);
 // in-degree of every node (multiplicity counted), parallel
 void host_indegree(const int32_t* col, int64_t e, int32_t n, uint32_t* indeg);
 

@@ -126,6 +126,13 @@ def test_parallel_colouring_matches_the_fifo_oracle_on_large_frontiers():
     rng = np.random.default_rng(11)
     n = 60000
     cases.append(G.from_edges(n, rng.integers(0, n, 45000), rng.integers(0, n, 45000)))  # thousands of small components
+    m = 150000  # components that outlast the transpose-free phase's edge budget / start at a sink / follow isolated nodes
+    cases.append(G.from_edges(m, np.arange(m - 1), np.arange(1, m)))          # a path: hundreds of thousands of levels
+    cases.append(G.from_edges(m, np.arange(1, m), np.arange(m - 1)))          # reversed: node 0 is a sink root
+    cases.append(G.from_edges(m, rng.integers(5, m, 400000), rng.integers(5, m, 400000)))  # nodes 0..4 isolated
+    src = np.concatenate([[0, 1], rng.integers(2, m, 400000)])
+    dst = np.concatenate([[1, 0], rng.integers(2, m, 400000)])
+    cases.append(G.from_edges(m, src, dst))                                   # tiny first component, giant one later
     for g in cases:
         assert (ppr.find_partitions_csr(g) == ob.oracle_find_partitions(g)).all()
 
