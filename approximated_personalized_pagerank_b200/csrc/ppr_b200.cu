@@ -391,23 +391,35 @@ static void storage_order(const int64_t* row_ptr, int32_t n, const uint8_t* colo
   }
 }
 
+// pprb200_debug_host_plan: the host front half alone (no device is touched), copied out for the CPU tests
+struct HostPlanOut {
+  int32_t* pos_of;      // [n] storage position or -1 (sink)
+  int32_t* rank_of;     // [n] rank label
+  int64_t* row_off;     // [n+1] (M+1 used)
+  uint32_t* enc;        // [E] column words in storage order
+  int32_t* item_pos;    // [item_cap]
+  int64_t* item_off;
+  int32_t* item_len;
+  int32_t item_cap;
+  int32_t* summary;     // [16] M, n_items, chunk, mid_deg, range_begin[2], range_end[2], item_begin[2][2], item_end[2][2]
+};
+
 static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour_in,
                                uint32_t max_L, uint32_t hub_threshold, int32_t rank, int32_t world, void* stream,
-                               pprb200_session** out, bool need_colour = true) {
+                               pprb200_session** out, bool need_colour = true, const HostPlanOut* plan_out = nullptr) {
   if (!out) return fail(PPRB200_ERR_PARAM, "out is NULL");
   *out = nullptr;
   if (max_L == 0) return fail(PPRB200_ERR_PARAM, "L must be positive");
   if (world < 1 || world > MAX_WORLD || rank < 0 || rank >= world) return fail(PPRB200_ERR_PARAM, "rank %d / world %d: need 0 <= rank < world <= %d", rank, world, MAX_WORLD);
   int rc = validate_csr(row_ptr, col, n);
   if (rc) return rc;
-  rc = device_ok();
-  if (rc) return rc;
+  if (!plan_out && (rc = device_ok())) return rc;
 
   const double t0 = now_ms();
   pprb200_session* s = new pprb200_session();
   std::memset(&s->peers, 0, sizeof(s->peers));
   std::memset(s->ipc_opened, 0, sizeof(s->ipc_opened));
-  pool_setup_once();
+  if (!plan_out) pool_setup_once();
   g_alloc_stream = (cudaStream_t)stream;
   s->n = n;
   s->max_L = max_L;
@@ -415,9 +427,11 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   s->rank = rank;
   s->world = world;
   s->stream = (cudaStream_t)stream;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (!plan_out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
 
   std::vector<uint8_t> colour((size_t)n);
   if (colour_in) std::memcpy(colour.data(), colour_in, (size_t)n);
@@ -526,6 +540,28 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   if (getenv("PPRB200_HOST_TIMING"))
     fprintf(stderr, "[pprb200] host prep %.2f ms: colour %.2f, storage order %.2f, rank labels %.2f, offsets+items %.2f, encode %.2f (%d threads)\n",
             s->prep_ms, t_col - t0, t_ord - t_col, t_rank - t_ord, t_items - t_rank, now_ms() - t_items, host_threads());
+  if (plan_out) {
+    const HostPlanOut& o = *plan_out;
+    if (o.pos_of) std::memcpy(o.pos_of, pos_of.data(), sizeof(int32_t) * (size_t)n);
+    if (o.rank_of) std::memcpy(o.rank_of, rank_of.data(), sizeof(int32_t) * (size_t)n);
+    if (o.row_off) for (int32_t p = 0; p <= M; p++) o.row_off[p] = row_off[(size_t)p];
+    if (o.enc && E) std::memcpy(o.enc, enc.data(), sizeof(uint32_t) * (size_t)E);
+    const int32_t ni = std::min<int32_t>(s->n_items, o.item_cap);
+    for (int32_t i = 0; i < ni; i++) {
+      if (o.item_pos) o.item_pos[i] = item_pos[(size_t)i];
+      if (o.item_off) o.item_off[i] = item_off[(size_t)i];
+      if (o.item_len) o.item_len[i] = item_len[(size_t)i];
+    }
+    if (o.summary) {
+      int32_t* q = o.summary;
+      q[0] = M; q[1] = s->n_items; q[2] = s->chunk; q[3] = s->mid_deg;
+      for (int c = 0; c < 2; c++) { q[4 + c] = s->range_begin[c]; q[6 + c] = s->range_end[c]; }
+      for (int c = 0; c < 2; c++)
+        for (int k = 0; k < 2; k++) { q[8 + 2 * c + k] = s->item_begin[c][k]; q[12 + 2 * c + k] = s->item_end[c][k]; }
+    }
+    delete s;
+    return PPRB200_OK;
+  }
 
   const double t1 = now_ms();
   const int Lp = roundup4((int)max_L);
@@ -1360,6 +1396,19 @@ int pprb200_ppr_exact(const int64_t* row_ptr, const int32_t* col, int32_t n, con
   if (kernel_ms) *kernel_ms = total_ms;
   cleanup();
   return PPRB200_OK;
+}
+
+// debug / CPU tests: the host front half of a session (colouring, storage order, rank labels, CSR encode, work items)
+// without touching a device. Every output pointer may be NULL.
+int pprb200_debug_host_plan(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour, uint32_t hub_threshold,
+                            int32_t rank, int32_t world, int32_t* pos_of, int32_t* rank_of, int64_t* row_off, uint32_t* enc,
+                            int32_t* item_pos, int64_t* item_off, int32_t* item_len, int32_t item_cap, int32_t* summary) {
+  HostPlanOut o;
+  o.pos_of = pos_of; o.rank_of = rank_of; o.row_off = row_off; o.enc = enc; o.item_pos = item_pos; o.item_off = item_off;
+  o.item_len = item_len; o.item_cap = item_cap; o.summary = summary;
+  pprb200_session* unused = nullptr;
+  std::lock_guard<std::mutex> lk(g_api_mutex);
+  return session_create_impl(row_ptr, col, n, colour, 1, hub_threshold, rank, world, nullptr, &unused, true, &o);
 }
 
 // which rank of `world` updates node v (-1: sinks, nobody), exactly as the sessions shard the work

@@ -142,6 +142,15 @@ int pprb200_shard_owner(const int64_t* row_ptr, const int32_t* col, int32_t n, c
 /* Kernels the last run enqueued on the session stream (bench.py's gpu_launches). */
 int pprb200_session_launches(pprb200_session* s, uint64_t* launches);
 
+/* Debug / CPU tests: the host front half of a session alone -- colouring (colour == NULL), storage order, rank labels, CSR
+ * encode, work items of rank `rank` of `world` -- without touching a device. pos_of[n] (storage position, -1 for sinks),
+ * rank_of[n], row_off[n+1] (M+1 used), enc[E] (column words), item_*[item_cap]; summary[16] = M, n_items, chunk, mid_deg,
+ * range_begin[2], range_end[2], item_begin[2][2], item_end[2][2]. Every output pointer may be NULL. */
+int pprb200_debug_host_plan(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour, uint32_t hub_threshold,
+                            int32_t rank, int32_t world, int32_t* pos_of, int32_t* rank_of, int64_t* row_off, uint32_t* enc,
+                            int32_t* item_pos, int64_t* item_off, int32_t* item_len, int32_t item_cap, int32_t* summary);
+
+
 /* Quality-evaluator yardstick: exact Personalized PageRank by power iteration for a batch of
  * sources -- replaces ppr::pprInternal::pprSingleSource (/root/reference/include/internal/pprSingleSource.h:28-75)
  * as include/benchmarkAlgorithm.h:91 calls it, once per sampled node. out_scores[i*n + v] = score of node v for
