@@ -4,7 +4,7 @@
 //   * Non-sink nodes live at "storage positions" p = 0..M-1 (colour-major, then class, then out-degree
 //     descending). Sinks own no storage: their basket is the constant {v: 1-d} (GRank) / {v: 1} (MC).
 //   * row_off[M+1] (int64) / col[E'] (uint32): CSR in storage order. A col word is
-//        sink successor      : 0x80000000 | dense id of the sink
+//        sink successor      : 0x80000000 | rank label of the sink
 //        non-sink successor  : storage position | colour << 30
 //   * Basket entries carry "rank labels": nodes numbered by in-degree descending (ties by dense id), so that the
 //     most popular keys are the smallest integers (merge_par.cuh indexes a dense accumulator with them).
@@ -40,8 +40,8 @@ struct RunState {
   int iter;                  // iterations executed so far
   long long m_prev, m_last;  // maxDiff of the two most recent iterations, 2^-61 fixed point
   long long cur_max;         // running max of the iteration in flight
-  unsigned int work[8];      // work-fetch counters, one per kernel stage
-  unsigned int qcount[4];    // overflow queue lengths (nodes that need a larger table)
+  unsigned int work[12];     // work-fetch counters, one per kernel stage
+  unsigned int qcount[8];    // overflow queue lengths (0-3: exact-order cascade, 4: merge_dense -> merge_par hand-over)
   unsigned long long node_iters, edge_reads, merged, cands, truncs, ties, abytes, requeues;
   unsigned long long walk_steps, walks, walk_bytes;
   unsigned int ws_next;      // bump allocator for the global-table workspace
@@ -51,7 +51,7 @@ struct RunState {
 
 // ------------------------------------------------------------------------------------------------
 // Multi-GPU: one process per GPU; every GPU holds the whole CSR and both basket buffers and owns
-// every world-th node of each class (interleaved over the degree-sorted storage order). A node's new basket is
+// a share of each (colour, class) list chosen longest-processing-time-first (storage_order). A node's new basket is
 // written locally and PUSHED into the same slot of every peer's buffer with plain stores through NVLink peer
 // mappings (cudaIpc) by the warp / CTA that produced it -- the allgather of the reference design is fused into the
 // merge / walk kernels' epilogue and overlaps the rest of the grid's work. Iterations are separated by a mailbox
@@ -68,6 +68,7 @@ struct PeerDev {
   int world, rank;
   unsigned char* buf[MAX_WORLD][2];  // peer basket buffers (entry [rank] = the local ones)
   Mailbox* mbox[MAX_WORLD];          // peer mailboxes: mbox[r][parity * MAX_WORLD + sender]
+  long long timeout_cycles;          // a barrier gives up after this many SM clocks (default ~30 s; PPRB200_PEER_TIMEOUT_MS)
 };
 
 // copy the freshly written slot of position p to every peer; `lane`/`nlanes` = the calling warp or CTA.
@@ -102,7 +103,7 @@ __device__ inline long long cross_gpu_barrier(const PeerDev& pd, unsigned long l
   for (int r = 0; r < pd.world; r++) {
     const Mailbox* m = pd.mbox[pd.rank] + par * MAX_WORLD + r;
     while (*reinterpret_cast<const volatile unsigned long long*>(&m->seq) != seq) {
-      if (clock64() - t0 > 60000000000ll) { *timed_out = 1; return best; }  // ~30 s: a peer died
+      if (clock64() - t0 > pd.timeout_cycles) { *timed_out = 1; return best; }  // a peer died: the host reports it (session_stats / fetch)
       __nanosleep(200);
     }
     __threadfence_system();

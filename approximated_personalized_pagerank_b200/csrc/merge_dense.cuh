@@ -1,0 +1,599 @@
+// merge_dense.cuh -- the fast path of the order-free merge step: one CTA per node, everything in shared memory.
+//
+// Same operator and the same sums as merge_par.cuh (grank.h:96-126, mccompletepathv2.h:211-250 with every product
+// rounded once to 2^-62 / 2^-59 fixed point, oracle/ppr_oracle.c hub mode), restructured around what the round-1
+// profile showed (profiles/r2/): the accumulate loops were bound by DIVERGENCE, not by memory or atomics -- with
+// 10-20 % tail labels per basket nearly every warp step executed the dense path, the sketch path and the
+// old-basket path one after the other -- and by ~37 % per-node overhead (two selects, three table sweeps).
+//
+//   * Pass 1 is ONE branch-free instruction stream for every entry -- cvt, address select, ATOMS.ADD low word, carry
+//     into the high word -- over three kinds of accumulators: rank label k < H owns a 64-bit fixed-point word; a
+//     tail label of the node's OLD basket ("pre" label: the best predictor of the new basket) owns the word of its
+//     home slot in the tail hash table; every other label shares a 32-bit sketch bucket that holds an UPPER bound of
+//     the sum (each product rounded up to 2^-30 / 2^-27): one atomic, no carry, and twice the buckets per byte.
+//   * Lanes walk the node's successor baskets as one stream of 16-byte quads (4 entries): 32 consecutive quads per
+//     warp step whatever the basket length, so all 32 lanes work (L = 100 gives 25 quads per basket: a warp per
+//     basket would idle 7 lanes) and the next step's three LDG.128 per lane are in flight while this one is added.
+//   * The cut is bounded from below by tau = the old basket's smallest score (or 3/4, 1/2, 1/16 of it), validated by
+//     counting: if at least L exact candidates (dense + pre labels) reach tau, no label below tau can be kept. A sketch
+//     bucket below tau holds no label that can be kept (strictly, ties included), so pass 2 -- needed only when some
+//     bucket survives -- re-reads the label words (L2-hot) and accumulates exactly the tail labels of the surviving
+//     buckets in the hash table. One radix select per node.
+//   * Anything that does not fit (more candidates / surviving tail labels than the shared arrays hold, a product
+//     that rounds to zero -- such a label is a candidate with score 0 and leaves no trace in a sum --, a sketch
+//     bucket that wraps, nodes split into several chunks) is handed to merge_par_kernel through a device queue:
+//     same sums, slower path.
+#pragma once
+#include "merge_par.cuh"
+
+namespace pprb200 {
+
+struct DenseParams {
+  MergeParams M;
+  const int* item_pos;          // work items of this launch: node position,
+  const long long* item_begin;  //   first successor (absolute offset into col),
+  const int* item_len;          //   number of successors
+  int n_items;
+  int item_base;                // global index of item 0 (queue entries are global item indices)
+  int chunk;                    // nodes above this out-degree are split into several items: not handled here
+  int work_idx;
+  unsigned int* fb_queue;       // items handed to merge_par_kernel
+  int fb_idx;                   // its length: st->qcount[fb_idx]
+  unsigned long long* prof;     // optional [gridDim.x * 8] phase cycle counters (PPRB200_PROF=1)
+};
+
+struct DenseShared {
+  ParShared P;   // scratch of the block reductions / radix select
+  int ncol;      // non-sink column words staged for the current tile
+  int bail;      // hand the node to the general kernel
+  int lvl[2];    // exact candidates >= theta0 / >= 0.75 theta0
+};
+
+template <int H, int R, int TCAP, int CMAX, int COLCAP>
+constexpr size_t dense_smem_bytes() {
+  return (size_t)H * 8 + (size_t)R * 4 + (size_t)CMAX * 12 + (size_t)TCAP * 14 + (size_t)COLCAP * 4 + (size_t)R / 8 + sizeof(DenseShared) + 16;
+}
+
+template <int H, int R, int TCAP, int CMAX, int COLCAP, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams P) {
+  constexpr int NW = THREADS / 32;
+  constexpr int TLIMIT = TCAP * 13 / 16 - THREADS;  // distinct tail labels admitted (concurrent inserts overshoot by < THREADS)
+  static_assert(TLIMIT >= 128, "tail table too small for this CTA size");
+  static_assert((R & (R - 1)) == 0 && (TCAP & (TCAP - 1)) == 0 && R % 32 == 0 && H % 32 == 0, "power-of-two tables");
+  static_assert(H + TCAP <= 65536, "tail list entries are 16 bit");
+  constexpr int RBITS = __builtin_ctz((unsigned)R);
+  // shared memory, as 32-bit words from the start of the dynamic segment (accumulator addresses are word indices):
+  //   dense words [0, 2H) | tail sums [2H, 2H + 2 TCAP) | sketch [.., + R) | everything else
+  constexpr unsigned W_TACC = 2u * H, W_SK = W_TACC + 2u * TCAP;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const MergeParams& M = P.M;
+  RunState* st = M.st;
+  if (!st->active) return;
+  unsigned int* const sw = reinterpret_cast<unsigned int*>(smem);
+  uint2* acc = reinterpret_cast<uint2*>(smem);                                  // dense labels
+  uint2* t_acc = reinterpret_cast<uint2*>(sw + W_TACC);                         // tail table: sums
+  unsigned int* sk = sw + W_SK;                                                 // sketch buckets (upper bounds, 2^-30 / 2^-27)
+  unsigned char* sp = reinterpret_cast<unsigned char*>(sk + R);
+  unsigned long long* c_bits = reinterpret_cast<unsigned long long*>(sp); sp += (size_t)CMAX * 8;   // candidates: score bits
+  int* c_id = reinterpret_cast<int*>(sp); sp += (size_t)CMAX * 4;                                   // candidates: labels
+  int* t_keys = reinterpret_cast<int*>(sp); sp += (size_t)TCAP * 4;          // tail table: label (inserted by pass 2) or ~label (pre)
+  uint32_t* s_col = reinterpret_cast<uint32_t*>(sp); sp += (size_t)COLCAP * 4;                      // staged column words
+  unsigned int* s_alive = reinterpret_cast<unsigned int*>(sp); sp += (size_t)R / 8;                 // buckets that may hold a kept label
+  unsigned short* t_list = reinterpret_cast<unsigned short*>(sp); sp += (size_t)TCAP * 2;           // occupied tail slots
+  sp = reinterpret_cast<unsigned char*>(((uintptr_t)sp + 7) & ~(uintptr_t)7);
+  DenseShared* DS = reinterpret_cast<DenseShared*>(sp);
+  ParShared* S = &DS->P;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int Lp = M.Lp, groups = Lp >> 2, L = M.L;
+  const double scale = (M.mode == MODE_GRANK) ? GRANK_HUB_SCALE : MC_HUB_SCALE;
+  const double inv = (M.mode == MODE_GRANK) ? GRANK_HUB_INV : MC_HUB_INV;
+  const double sk_inv = inv * 4294967296.0;  // one sketch unit
+  const int* __restrict__ dense_of = M.g.dense_of;
+  const size_t slotb = slot_bytes(Lp);
+
+  for (int i = tid; i < H; i += THREADS) acc[i] = make_uint2(0u, 0u);
+  for (int i = tid; i < R; i += THREADS) sk[i] = 0u;
+  for (int i = tid; i < TCAP; i += THREADS) { t_keys[i] = KEY_EMPTY; t_acc[i] = make_uint2(0u, 0u); }
+  if (tid == 0) { S->tcount = 0; S->spilled = 0; }
+  __syncthreads();
+
+  const unsigned char* const rbuf0 = M.buf[st->slot[0]];  // current baskets of colour 0 / 1
+  const unsigned char* const rbuf1 = M.buf[st->slot[1]];
+  const int write_slot = st->slot[M.colour] ^ 1;
+  unsigned long long s_merged = 0, s_edges = 0, s_cands = 0, s_truncs = 0, s_ties = 0, s_bytes = 0, s_nodes = 0, s_requeue = 0;
+
+  auto home_of = [](unsigned int hk) -> unsigned int { return hk & (unsigned)(TCAP - 1); };
+  auto bucket_of = [](unsigned int hk) -> unsigned int { return hk >> (32 - RBITS); };
+  // exact accumulate of a tail label (pass 2); false when the key is absent and the table is closed
+  auto tail_add = [&](int k, unsigned long long x) -> bool {
+    unsigned int h = home_of(hash_key(k));
+    volatile int* keys = t_keys;
+    for (;;) {
+      const int cur = keys[h];
+      if (cur == k) break;
+      if (cur == KEY_EMPTY) {
+        if (*reinterpret_cast<volatile int*>(&S->tcount) >= TLIMIT) return false;
+        const int old = atomicCAS(&t_keys[h], KEY_EMPTY, k);
+        if (old == KEY_EMPTY) { const int pos = atomicAdd(&S->tcount, 1); t_list[pos] = (unsigned short)h; break; }
+        if (old == k) break;
+      }
+      h = (h + 1) & (TCAP - 1);
+    }
+    fixed_add_shared(&t_acc[h], x);
+    return true;
+  };
+  // one contribution (pass 1, any thread): dense word, pre word or sketch bucket. Returns true when it must not be
+  // trusted (a product that rounds to zero, a sketch bucket that wrapped): the node is handed over.
+  auto contribute = [&](int k, unsigned long long xf) -> bool {
+    const unsigned int hk = hash_key(k);
+    const unsigned int hm = home_of(hk);
+    const bool dense = (unsigned)k < (unsigned)H;
+    const bool exact = dense || t_keys[hm] == ~k;
+    const unsigned int wi = dense ? 2u * (unsigned)k : (exact ? W_TACC + 2u * hm : W_SK + bucket_of(hk));
+    const unsigned int xlo = (unsigned int)xf, xhi = (unsigned int)(xf >> 32);
+    const unsigned int lo = exact ? xlo : xhi + 1u;  // sketch: the product rounded UP to one unit
+    const unsigned int old = atomicAdd(sw + wi, lo);
+    const unsigned int carry = (old + lo) < old ? 1u : 0u;
+    const unsigned int hi = exact ? xhi + carry : 0u;
+    if (hi) atomicAdd(sw + wi + 1u, hi);
+    return xf == 0ull || (!exact && carry);
+  };
+  auto alive = [&](unsigned int hk) -> bool {
+    const unsigned int b = bucket_of(hk);
+    return (s_alive[b >> 5] >> (b & 31)) & 1u;
+  };
+  // pass 2: does label k (any value) need its exact sum from this sweep? tail label, not pre, bucket alive
+  auto wanted = [&](int k) -> bool {
+    if (k < H) return false;
+    const unsigned int hk = hash_key(k);
+    return t_keys[home_of(hk)] != ~k && alive(hk);
+  };
+  auto word_score = [&](uint2 a) -> double { return (double)(long long)(((unsigned long long)a.y << 32) | a.x) * inv; };
+  // append to the compact candidate arrays (all 32 lanes call)
+  auto append = [&](bool ok, unsigned long long bits, int id) {
+    const unsigned m = __ballot_sync(FULL, ok);
+    if (m) {
+      int basep = 0;
+      if (lane == (int)(__ffs(m) - 1)) basep = atomicAdd(&S->ncand, __popc(m));
+      basep = __shfl_sync(FULL, basep, __ffs(m) - 1);
+      if (ok) {
+        const int pos = basep + __popc(m & ((1u << lane) - 1u));
+        if (pos < CMAX) { c_bits[pos] = bits; c_id[pos] = id; }
+      }
+    }
+  };
+
+  unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long t_last = clock64();
+#define DPROF_MARK(i) do { if (P.prof && tid == 0) { const long long t_now = clock64(); pc[i] += (unsigned long long)(t_now - t_last); t_last = t_now; } } while (0)
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) { S->item = atomicAdd(&st->work[P.work_idx], 1u); DS->bail = 0; S->ncand = 0; DS->lvl[0] = 0; DS->lvl[1] = 0; }
+    __syncthreads();
+    const unsigned int item = S->item;
+    if (item >= (unsigned)P.n_items) break;
+    DPROF_MARK(0);
+    const int p = P.item_pos[item];
+    const long long cb = P.item_begin[item];
+    const int clen = P.item_len[item];
+    const long long deg = M.g.row_off[p + 1] - M.g.row_off[p];
+    if (deg > (long long)P.chunk) {  // a chunk of a split hub: the general kernel's job
+      if (tid == 0) P.fb_queue[atomicAdd(&st->qcount[P.fb_idx], 1u)] = (unsigned int)P.item_base + item;
+      continue;
+    }
+    const int self_id = M.g.label[p];
+    const double f = M.damping / (double)(unsigned long long)deg;
+    const double fscale = f * scale;  // (x * f) * 2^s == x * (f * 2^s): scaling by a power of two commutes with the rounding
+    const double self0 = (M.mode == MODE_GRANK) ? M.self_grank : 1.0;
+    const unsigned long long xself = (unsigned long long)__double2ll_rn(self0 * scale);
+    const unsigned long long xsink = (unsigned long long)__double2ll_rn(((M.mode == MODE_GRANK) ? M.self_grank : 1.0) * fscale);
+    const unsigned char* old = M.buf[write_slot ^ 1] + (size_t)p * slotb;
+
+    // The old basket: its smallest score (when full) is the first guess of the new cut; its tail labels -- and the node's
+    // own label -- become "pre" labels: exact accumulators at the home slots of the tail table (first come first served;
+    // a label that finds its home taken stays an ordinary tail label).
+    double theta0 = 0.0;
+    {
+      const int* oid = reinterpret_cast<const int*>(old);
+      const double* osc = reinterpret_cast<const double*>(old + (size_t)Lp * 4);
+      unsigned long long mn = ~0ull;
+      long long cntv = 0;
+      for (int i = tid; i < Lp + 1; i += THREADS) {
+        const int k = i < Lp ? oid[i] : self_id;
+        if (i < Lp && k >= 0) { const unsigned long long b = (unsigned long long)__double_as_longlong(osc[score_index(i, Lp)]); mn = b < mn ? b : mn; cntv++; }
+        if (k >= H) {
+          const unsigned int hm = home_of(hash_key(k));
+          if (atomicCAS(&t_keys[hm], KEY_EMPTY, ~k) == KEY_EMPTY) t_list[atomicAdd(&S->tcount, 1)] = (unsigned short)hm;
+        }
+      }
+      block_reduce_min_sum(mn, cntv, S->red_a);
+      if (cntv >= L) theta0 = __longlong_as_double((long long)mn);
+    }
+    const int npre = S->tcount;  // (block_reduce_min_sum ends with a barrier)
+    bool bad = false;            // this thread saw a contribution that must not be trusted
+    if (tid == 0) {              // the self term (grank.h:101 / mccompletepathv2.h:226)
+      bad |= contribute(self_id, xself);
+    }
+
+    // One sweep over the node's successor baskets.
+    //   pass 1: every entry into its dense word, pre word or sketch bucket
+    //   pass 2: tail labels of surviving buckets exactly into the tail table (label words only; scores fetched on a hit)
+    unsigned int merged = 0;
+    auto sweep = [&](const int pass) {
+      const int sj = (NW * 32) / groups, sg = (NW * 32) - sj * groups;  // one warp-grid step in (basket, quad) coordinates
+      for (int t0 = 0; t0 < clen; t0 += COLCAP) {
+        const int tlen = clen - t0 < COLCAP ? clen - t0 : COLCAP;
+        __syncthreads();
+        if (tid == 0) DS->ncol = 0;
+        __syncthreads();
+        // stage the tile's non-sink column words; a sink's basket is the constant {s: 1-d} / {s: 1}: added right here
+        for (int j0 = 0; j0 < tlen; j0 += THREADS) {
+          const int j = j0 + tid;
+          const uint32_t c = j < tlen ? M.g.col[cb + t0 + j] : COL_SINK;
+          const bool ns = !(c & COL_SINK);
+          if (j < tlen && !ns) {
+            const int k = (int)(c & ~COL_SINK);
+            if (pass == 1) {
+              merged++;
+              bad |= contribute(k, xsink);
+            } else if (wanted(k)) {
+              if (!tail_add(k, xsink)) S->spilled = 1;
+            }
+          }
+          const unsigned m = __ballot_sync(FULL, ns);
+          if (m) {
+            int base = 0;
+            if (lane == (int)(__ffs(m) - 1)) base = atomicAdd(&DS->ncol, __popc(m));
+            base = __shfl_sync(FULL, base, __ffs(m) - 1);
+            if (ns) s_col[base + __popc(m & ((1u << lane) - 1u))] = c;
+          }
+        }
+        __syncthreads();
+        const int total = DS->ncol * groups;  // quads of this tile
+        int q = w * 32 + lane;
+        int j = q / groups, g = q - j * groups;
+        auto base_of = [&](int jj) -> const unsigned char* {
+          const uint32_t cc = s_col[jj];
+          return (((cc >> COL_COLOUR_SHIFT) & 1u) ? rbuf1 : rbuf0) + (size_t)(cc & COL_POS_MASK) * slotb;
+        };
+        if (pass == 1) {
+          int4 id0 = make_int4(-1, -1, -1, -1);
+          double2 a0 = make_double2(0.0, 0.0), b0 = a0;
+          if (q < total) {
+            const unsigned char* bp = base_of(j) + (size_t)g * 16;
+            id0 = __ldg(reinterpret_cast<const int4*>(bp));
+            a0 = __ldg(reinterpret_cast<const double2*>(bp + (size_t)Lp * 4));
+            b0 = __ldg(reinterpret_cast<const double2*>(bp + (size_t)Lp * 8));
+          }
+          for (int q0 = w * 32; q0 < total; q0 += NW * 32) {
+            // next step's quad
+            q += NW * 32; j += sj; g += sg;
+            if (g >= groups) { g -= groups; j++; }
+            int4 id1 = make_int4(-1, -1, -1, -1);
+            double2 a1 = make_double2(0.0, 0.0), b1 = a1;
+            if (q < total) {
+              const unsigned char* bp = base_of(j) + (size_t)g * 16;
+              id1 = __ldg(reinterpret_cast<const int4*>(bp));
+              a1 = __ldg(reinterpret_cast<const double2*>(bp + (size_t)Lp * 4));
+              b1 = __ldg(reinterpret_cast<const double2*>(bp + (size_t)Lp * 8));
+            }
+            const int ids[4] = {id0.x, id0.y, id0.z, id0.w};
+            const double xs[4] = {a0.x, a0.y, b0.x, b0.y};
+            // (invalid entries: id -1, arbitrary score bytes -- computed on, never added)
+            unsigned int wi[4], lo[4], xhi[4], oldv[4];
+            bool ex[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const int k = ids[e];
+              const unsigned long long xf = (unsigned long long)__double2ll_rn(xs[e] * fscale);
+              const unsigned int hk = hash_key(k);
+              const unsigned int hm = home_of(hk);
+              const bool dense = (unsigned)k < (unsigned)H;
+              ex[e] = dense || t_keys[hm] == ~k;
+              wi[e] = dense ? 2u * (unsigned)k : (ex[e] ? W_TACC + 2u * hm : W_SK + bucket_of(hk));
+              xhi[e] = (unsigned int)(xf >> 32);
+              lo[e] = ex[e] ? (unsigned int)xf : xhi[e] + 1u;
+              bad |= k >= 0 && xf == 0ull;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; e++) oldv[e] = ids[e] >= 0 ? atomicAdd(sw + wi[e], lo[e]) : 0u;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const unsigned int carry = (oldv[e] + lo[e]) < oldv[e] ? 1u : 0u;
+              const unsigned int hi = ex[e] ? xhi[e] + carry : 0u;
+              if (ids[e] >= 0) {
+                if (hi) atomicAdd(sw + wi[e] + 1u, hi);
+                bad |= !ex[e] && carry;
+              }
+            }
+            merged += (ids[0] >= 0) + (ids[1] >= 0) + (ids[2] >= 0) + (ids[3] >= 0);
+            id0 = id1; a0 = a1; b0 = b1;
+          }
+        } else {
+          int4 id0 = make_int4(-1, -1, -1, -1);
+          if (q < total) id0 = __ldg(reinterpret_cast<const int4*>(base_of(j) + (size_t)g * 16));
+          for (int q0 = w * 32; q0 < total; q0 += NW * 32) {
+            const int jc = j, gc = g;
+            q += NW * 32; j += sj; g += sg;
+            if (g >= groups) { g -= groups; j++; }
+            int4 id1 = make_int4(-1, -1, -1, -1);
+            if (q < total) id1 = __ldg(reinterpret_cast<const int4*>(base_of(j) + (size_t)g * 16));
+            const int ids[4] = {id0.x, id0.y, id0.z, id0.w};
+            bool hit[4];
+            bool mine = false;
+#pragma unroll
+            for (int e = 0; e < 4; e++) { hit[e] = wanted(ids[e]); mine |= hit[e]; }
+            if (__any_sync(FULL, mine)) {  // most quads hold no surviving tail label: one vote skips them
+              if (mine) {
+                const unsigned char* bp = base_of(jc) + (size_t)gc * 16;
+                const double2 sa = __ldg(reinterpret_cast<const double2*>(bp + (size_t)Lp * 4));
+                const double2 sb = __ldg(reinterpret_cast<const double2*>(bp + (size_t)Lp * 8));
+                const double xs[4] = {sa.x, sa.y, sb.x, sb.y};
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                  if (hit[e] && !tail_add(ids[e], (unsigned long long)__double2ll_rn(xs[e] * fscale))) S->spilled = 1;
+              }
+            }
+            id0 = id1;
+          }
+        }
+      }
+    };
+
+    sweep(1);
+    DPROF_MARK(1);
+    bool bail = __syncthreads_or(bad ? 1 : 0) != 0;  // (also: pass 1 complete)
+
+    // ---- exact candidates (dense + pre labels) that reach the bound -> compact (score bits, label) arrays ----
+    // compacted from thb = theta0 / 2 up; tau = the highest of (theta0, 3/4 theta0, theta0 / 2) that L of them reach
+    bool dropped_local = false;  // this thread saw a candidate that is not in the compact arrays
+    double th = theta0 * 0.5;
+    double tau = th;
+    int n = 0;
+    if (!bail) {
+      for (int attempt = 0;; attempt++) {
+        dropped_local = false;
+        const unsigned long long thb = (unsigned long long)__double_as_longlong(th);
+        const unsigned long long la = (unsigned long long)__double_as_longlong(theta0), lb = (unsigned long long)__double_as_longlong(theta0 * 0.75);
+        int ca = 0, cq = 0;
+        for (int i0 = 0; i0 < H; i0 += THREADS) {
+          const int i = i0 + tid;
+          const uint2 a = i < H ? acc[i] : make_uint2(0u, 0u);
+          const bool nz = (a.x | a.y) != 0u;
+          const unsigned long long bits = (unsigned long long)__double_as_longlong(word_score(a));
+          const bool ok = nz && bits >= thb;
+          dropped_local |= nz && !ok;
+          ca += ok && bits >= la;
+          cq += ok && bits >= lb;
+          append(ok, bits, i);
+        }
+        for (int i0 = 0; i0 < npre; i0 += THREADS) {
+          const int i = i0 + tid;
+          bool ok = false;
+          unsigned long long bits = 0ull;
+          int id = 0;
+          if (i < npre) {
+            const int sl = t_list[i];
+            const uint2 a = t_acc[sl];
+            id = ~t_keys[sl];
+            const bool nz = (a.x | a.y) != 0u;
+            bits = (unsigned long long)__double_as_longlong(word_score(a));
+            ok = nz && bits >= thb;
+            dropped_local |= nz && !ok;
+            ca += ok && bits >= la;
+            cq += ok && bits >= lb;
+          }
+          append(ok, bits, id);
+        }
+        if (attempt == 0 && theta0 > 0.0) {
+          ca = warp_sum_int(ca);
+          cq = warp_sum_int(cq);
+          if (lane == 0) { if (ca) atomicAdd(&DS->lvl[0], ca); if (cq) atomicAdd(&DS->lvl[1], cq); }
+        }
+        __syncthreads();
+        n = S->ncand;
+        tau = th;
+        if (n >= L || th == 0.0) {
+          if (attempt == 0 && theta0 > 0.0) tau = DS->lvl[0] >= L ? theta0 : (DS->lvl[1] >= L ? theta0 * 0.75 : th);
+          break;
+        }
+        __syncthreads();
+        if (tid == 0) S->ncand = 0;  // fewer than L candidates reach the bound: it is none -- relax it and compact again
+        __syncthreads();
+        th = attempt == 0 ? th * 0.125 : 0.0;
+      }
+      if (n > CMAX) bail = true;
+    }
+    const unsigned long long thb = (unsigned long long)__double_as_longlong(th);  // what the compact arrays were filtered with
+    DPROF_MARK(2);
+
+    // ---- sketch buckets that can hold a kept label: upper bound >= tau (tau > 0 only with >= L candidates above it) ----
+    if (!bail) {
+      int any = 0;
+      for (int i0 = 0; i0 < R; i0 += THREADS) {
+        const int i = i0 + tid;
+        const unsigned int a = i < R ? sk[i] : 0u;
+        const bool al = a != 0u && (double)a * sk_inv >= tau;
+        dropped_local |= a != 0u && !al;
+        const unsigned m = __ballot_sync(FULL, al);
+        if (lane == 0 && i < R) s_alive[i >> 5] = m;
+        any |= m != 0u;
+      }
+      any = __syncthreads_or(any);
+      DPROF_MARK(3);
+      if (any) {
+        sweep(2);
+        __syncthreads();
+        if (S->spilled) bail = true;
+        if (!bail) {
+          const int nt0 = S->tcount;
+          for (int i0 = npre; i0 < nt0; i0 += THREADS) {
+            const int i = i0 + tid;
+            bool ok = i < nt0;
+            unsigned long long bits = 0ull;
+            int id = 0;
+            if (ok) {
+              const int sl = t_list[i];
+              id = t_keys[sl];
+              bits = (unsigned long long)__double_as_longlong(word_score(t_acc[sl]));
+              ok = bits >= thb;
+              dropped_local |= !ok;
+            }
+            append(ok, bits, id);
+          }
+          __syncthreads();
+          n = S->ncand;
+          if (n > CMAX) bail = true;
+        }
+      }
+      DPROF_MARK(4);
+    }
+
+    int kept = 0, old_cnt = 0;
+    if (!bail) {
+      // ---- keepTop(L) with the canonical tie-break (pprInternal.h:109-137) ----
+      const unsigned long long* kb = c_bits;
+      const int* ki = c_id;
+      Threshold thr;
+      thr.bits = thb;  // n <= L: everything that reached the bound is kept, nothing below it is
+      thr.id_max = 0x7fffffff;
+      kept = n;
+      auto all = [](int) { return true; };
+      const int dropped_any = __syncthreads_or(dropped_local ? 1 : 0);
+      if (n > L) {
+        kept = L;
+        bool tie;
+        int krem;
+        auto keyfn = [&](int i) { return kb[i]; };
+        int ntied = 0;
+        thr.bits = block_radix_select(n, L, keyfn, all, S, &tie, &krem, &ntied);
+        if (tie) {
+          const unsigned long long tb = thr.bits;
+          if (ntied <= 32) {
+            auto densefn = [&](int i) { return dense_of[ki[i]]; };
+            thr.id_max = block_small_tie_cut(n, krem, tb, keyfn, all, densefn, S);
+          } else {
+            auto idkey = [&](int i) { return (unsigned long long)(0x7fffffff - dense_of[ki[i]]); };
+            auto tied = [&](int i) { return kb[i] == tb; };
+            bool tie2;
+            int krem2;
+            const unsigned long long tid_key = block_radix_select(n, krem, idkey, tied, S, &tie2, &krem2);
+            thr.id_max = 0x7fffffff - (int)tid_key;
+          }
+          s_ties += (tid == 0);
+        }
+        s_truncs += (tid == 0);
+      } else if (dropped_any) {
+        s_truncs += (tid == 0);  // exactly L candidates reached the bound and others did not: a cut without a boundary tie
+      }
+      auto selected = [&](unsigned long long bits, int label) -> bool {
+        return bits > thr.bits || (bits == thr.bits && (thr.id_max == 0x7fffffff || dense_of[label] <= thr.id_max));
+      };
+      DPROF_MARK(5);
+      // ---- write B'_v ----
+      unsigned char* out = M.buf[write_slot] + (size_t)p * slotb;
+      int* out_ids = reinterpret_cast<int*>(out);
+      double* out_sc = reinterpret_cast<double*>(out + (size_t)Lp * 4);
+      if (tid == 0) S->out_pos = 0;
+      __syncthreads();
+      long long dsum = 0;
+      for (int i = tid; i < n; i += THREADS) {
+        const unsigned long long bits = kb[i];
+        const int id = ki[i];
+        if (selected(bits, id)) {
+          const int pos = atomicAdd(&S->out_pos, 1);
+          const double v = __longlong_as_double((long long)bits);
+          out_ids[pos] = id;
+          out_sc[score_index(pos, Lp)] = v;  // already multiplied by f = d/outdeg
+          dsum += fix_norm(v);
+        }
+      }
+      for (int i = kept + tid; i < Lp; i += THREADS) out_ids[i] = KEY_EMPTY;
+      // ---- norm1 against the old basket (pprInternal.h:147-165) ----
+      if (M.do_norm) {
+        for (int g = tid; g < groups; g += THREADS) {
+          BasketFrag fr;
+          load_frag(old, Lp, g, &fr);
+          const int ids[4] = {fr.id.x, fr.id.y, fr.id.z, fr.id.w};
+          const double xs[4] = {fr.sa.x, fr.sa.y, fr.sb.x, fr.sb.y};
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            if (ids[e] >= 0) {
+              old_cnt++;
+              bool found = false;
+              uint2 a = make_uint2(0u, 0u);
+              if ((unsigned)ids[e] < (unsigned)H) {
+                a = acc[ids[e]];
+                found = (a.x | a.y) != 0u;
+              } else {
+                // pre label: exact word at (or, its home taken, not at) the home slot; otherwise in the table iff its
+                // bucket survived -- if not, its new score is below the cut
+                for (unsigned int h = home_of(hash_key(ids[e]));; h = (h + 1) & (TCAP - 1)) {
+                  const int cur = t_keys[h];
+                  if (cur == ids[e] || cur == ~ids[e]) { a = t_acc[h]; found = (a.x | a.y) != 0u; break; }
+                  if (cur == KEY_EMPTY) break;
+                }
+              }
+              const double nv_ = word_score(a);
+              const bool in_new = found && selected((unsigned long long)__double_as_longlong(nv_), ids[e]);
+              if (in_new) dsum += fix_norm(fabs(nv_ - xs[e])) - fix_norm(nv_);
+              else dsum += fix_norm(xs[e]);
+            }
+          }
+        }
+        long long oc = old_cnt;
+        block_reduce_sum2(dsum, oc, S->red_a);
+        old_cnt = (int)oc;
+        if (tid == 0 && dsum > 0) atomicMax(&st->cur_max, dsum);
+      }
+      __syncthreads();
+      publish_slot(M.peers, write_slot, (size_t)p * slotb, slotb, tid, THREADS);
+    }
+    DPROF_MARK(6);
+    // ---- leave the tables clean ----
+    __syncthreads();
+    for (int i = tid; i < H; i += THREADS) acc[i] = make_uint2(0u, 0u);
+    for (int i = tid; i < R; i += THREADS) sk[i] = 0u;
+    {
+      const int nt = S->tcount;
+      for (int i = tid; i < nt; i += THREADS) {
+        const int s = t_list[i];
+        t_keys[s] = KEY_EMPTY;
+        t_acc[s] = make_uint2(0u, 0u);
+      }
+    }
+    if (bail) {
+      // partial sums dropped; merge_par_kernel runs the node from scratch (same sums, global table)
+      if (tid == 0) { P.fb_queue[atomicAdd(&st->qcount[P.fb_idx], 1u)] = (unsigned int)P.item_base + item; s_requeue++; }
+    } else {
+      const unsigned long long mg = (unsigned long long)block_reduce_sum_ll((long long)merged, S->red_a);
+      if (tid == 0) {
+        M.ncand[p] = 0;
+        s_merged += mg;
+        s_edges += (unsigned long long)clen;
+        s_cands += (unsigned long long)n;
+        s_nodes += 1;
+        s_bytes += 12ull * mg + 4ull * (unsigned long long)clen + 12ull * (unsigned long long)old_cnt + 12ull * (unsigned long long)kept + 4ull + 16ull;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) { S->tcount = 0; S->spilled = 0; }
+    DPROF_MARK(7);
+  }
+#undef DPROF_MARK
+  if (P.prof && tid == 0)
+    for (int i = 0; i < 8; i++) atomicAdd(&P.prof[(size_t)blockIdx.x * 8 + i], pc[i]);
+  if (tid == 0) {
+    if (s_nodes) atomicAdd(&st->node_iters, s_nodes);
+    if (s_edges) atomicAdd(&st->edge_reads, s_edges);
+    if (s_merged) atomicAdd(&st->merged, s_merged);
+    if (s_cands) atomicAdd(&st->cands, s_cands);
+    if (s_truncs) atomicAdd(&st->truncs, s_truncs);
+    if (s_ties) atomicAdd(&st->ties, s_ties);
+    if (s_bytes) atomicAdd(&st->abytes, s_bytes);
+    if (s_requeue) atomicAdd(&st->requeues, s_requeue);
+  }
+}
+
+}  // namespace pprb200

@@ -44,6 +44,8 @@ struct ParParams {
   unsigned int* node_done;     // [M] chunks completed
   int n_ids;                   // label space (identity hashing when the table covers it)
   int use_sketch;              // two-pass merge with the tail sketch for single-item nodes
+  const unsigned int* item_queue;  // nullable: item indices handed over by merge_dense_kernel (its overflow / split hubs),
+  int queue_idx;                   //   st->qcount[queue_idx] of them; null: items 0 .. n_items-1
   unsigned long long* prof;    // optional [gridDim.x * 8] phase cycle counters (PPRB200_PROF=1)
 };
 
@@ -393,11 +395,15 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 3 : 1)) merge_par_k
   unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long t_last = clock64();
 #define PROF_MARK(i) do { if (P.prof && tid == 0) { const long long t_now = clock64(); pc[i] += (unsigned long long)(t_now - t_last); t_last = t_now; } } while (0)
+  const unsigned int n_work = P.item_queue ? st->qcount[P.queue_idx] : (unsigned)P.n_items;
   for (;;) {
-    if (tid == 0) S->item = atomicAdd(&st->work[P.work_idx], 1u);
+    if (tid == 0) {
+      const unsigned int idx = atomicAdd(&st->work[P.work_idx], 1u);
+      S->item = idx >= n_work ? 0xffffffffu : (P.item_queue ? P.item_queue[idx] : idx);
+    }
     __syncthreads();
     const unsigned int item = S->item;
-    if (item >= (unsigned)P.n_items) break;
+    if (item == 0xffffffffu) break;
     PROF_MARK(0);
     const int p = P.item_pos[item];
     const long long cb = P.item_begin[item];
@@ -769,9 +775,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 3 : 1)) merge_par_k
       if (cntv >= L) theta0 = __longlong_as_double((long long)mn);
     }
     // compaction with the warm-start filter; returns the candidate count (S->ncand), positions start at S->ncand = 0
+    double theta_used = 0.0;  // lower bound the compact arrays were filtered with
     auto compact_filtered = [&](bool from_dense, bool from_tail, bool from_pre = false) -> int {
       double th = theta0 * 0.5;
       for (int attempt = 0;; attempt++) {
+        theta_used = th;
         dropped_local = false;
         __syncthreads();
         if (tid == 0) S->ncand = 0;
@@ -945,7 +953,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 3 : 1)) merge_par_k
         ki = cids;
       }
       Threshold th;
-      th.bits = 0ull;
+      // n <= L: every candidate that reached the filter's bound is kept and nothing below it is (norm1 asks about those)
+      th.bits = use_global ? 0ull : (unsigned long long)__double_as_longlong(theta_used);
       th.id_max = 0x7fffffff;
       kept = n;
       auto all = [](int) { return true; };

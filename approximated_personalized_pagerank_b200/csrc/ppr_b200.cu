@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -16,6 +17,7 @@
 #include "mc_walk.cuh"
 #include "ppr_exact.cuh"
 #include "merge_par.cuh"
+#include "merge_dense.cuh"
 #include "ppr_internal.h"
 
 namespace pprb200 {
@@ -60,9 +62,10 @@ __global__ void pool_init_kernel(unsigned char* pool, size_t tbl_bytes, unsigned
 __global__ void phase_end_kernel(RunState* st, int clear_stats, int flip_both, PeerDev peers, int barrier) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     // multi-GPU: every rank's pushes of this phase have landed before anybody reads them (or overwrites their source)
-    if (barrier && peers.world > 1) cross_gpu_barrier(peers, ++st->barrier_seq, 0, &st->peer_timeout);
-    for (int i = 0; i < 8; i++) st->work[i] = 0;
-    for (int i = 0; i < 4; i++) st->qcount[i] = 0;
+    if (barrier && peers.world > 1 && !st->peer_timeout) cross_gpu_barrier(peers, ++st->barrier_seq, 0, &st->peer_timeout);
+    if (st->peer_timeout) st->active = 0;  // a dead peer: the remaining launches return at once, the host reports the error
+    for (int i = 0; i < 12; i++) st->work[i] = 0;
+    for (int i = 0; i < 8; i++) st->qcount[i] = 0;
     if (clear_stats) {
       st->node_iters = st->edge_reads = st->merged = st->cands = st->abytes = st->requeues = 0;
     }
@@ -73,12 +76,13 @@ __global__ void phase_end_kernel(RunState* st, int clear_stats, int flip_both, P
 // end of GRank iteration `it` (0-based) on `colour`: grank.h:129-140 + the loop test of :92
 __global__ void iter_end_kernel(RunState* st, int colour, double tolerance, PeerDev peers) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    for (int i = 0; i < 8; i++) st->work[i] = 0;
-    for (int i = 0; i < 4; i++) st->qcount[i] = 0;
+    for (int i = 0; i < 12; i++) st->work[i] = 0;
+    for (int i = 0; i < 8; i++) st->qcount[i] = 0;
     if (!st->active) return;
     // multi-GPU: barrier + allreduce(max) of the iteration's max-diff in one mailbox round; every rank takes the
     // same decision below, so converged runs skip the remaining barriers consistently
     if (peers.world > 1) st->cur_max = cross_gpu_barrier(peers, ++st->barrier_seq, st->cur_max, &st->peer_timeout);
+    if (st->peer_timeout) { st->active = 0; return; }
     st->slot[colour] ^= 1;
     st->iter++;
     st->m_prev = st->m_last;
@@ -191,6 +195,9 @@ struct pprb200_session {
   int item_begin[2][2] = {{0, 0}, {0, 0}}, item_end[2][2] = {{0, 0}, {0, 0}};
   int n_items = 0;
   int chunk = 4096, mid_deg = 64;
+  int hub_items[2] = {0, 0};          // leading items of the big list that are chunks of split hubs (out-degree > chunk)
+  bool use_dense = true;              // merge_dense_kernel for single-item nodes (PPRB200_DENSE=0: merge_par only)
+  int dense_threads = 1024;           // CTA size of the big instantiation (PPRB200_DENSE_THREADS)
   int* d_item_pos = nullptr;
   long long* d_item_off = nullptr;
   int* d_item_len = nullptr;
@@ -217,6 +224,7 @@ struct pprb200_session {
   unsigned char* d_buf[2] = {nullptr, nullptr};
   size_t buf_bytes = 0;
   unsigned int* d_queue[4] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned int* d_fb_queue = nullptr;  // [n_items] items merge_dense hands over to merge_par
   int* d_ncand = nullptr;
   RunState* d_state = nullptr;
   unsigned long long* d_final_stats = nullptr;
@@ -244,6 +252,9 @@ struct pprb200_session {
   uint64_t launch_count = 0;  // kernels enqueued by the last run
   double prep_ms = 0, h2d_ms = 0;
 };
+
+// L as the kernels see it: keepTop(L) is the identity once L >= n (a basket holds at most n distinct keys)
+static uint32_t effective_L(uint32_t L, int32_t n) { return std::min<uint32_t>(L, (uint32_t)std::max<int32_t>(n, 1)); }
 
 static int device_ok() {
   int cnt = 0;
@@ -311,7 +322,7 @@ static void session_free(pprb200_session* s) {
   void* plain[] = {s->d_seq_list, s->d_row_off, s->d_col, s->d_label, s->d_pos_of, s->d_dense_of, s->d_colour, s->d_queue[0], s->d_queue[1],
                    s->d_queue[2], s->d_queue[3], s->d_ncand, s->d_state, s->d_final_stats, s->d_ws, s->d_out_ids, s->d_out_scores,
                    s->d_out_cnt, s->d_item_pos, s->d_item_off, s->d_item_len, s->d_pool, s->d_walk_ws, s->d_prof, s->d_tbl_inuse,
-                   s->d_tbl_count, s->d_node_tbl, s->d_node_done};
+                   s->d_tbl_count, s->d_node_tbl, s->d_node_done, s->d_fb_queue};
   for (void* q : plain) dev_free(q);
   for (int i = 0; i < 2; i++) if (s->ev_walk[i]) cudaEventDestroy(s->ev_walk[i]);
   for (int i = 0; i < 2; i++) { if (s->aux[i]) cudaStreamDestroy(s->aux[i]); if (s->ev_join[i]) cudaEventDestroy(s->ev_join[i]); }
@@ -325,8 +336,15 @@ static void session_free(pprb200_session* s) {
 // Largest out-degree of the mid class (128-thread CTAs, H = TCAP = 2048). The larger the label space, the larger the
 // share of tail labels per basket and the earlier the 2048-slot tail table fills up (measured on R-MAT 16..22,
 // profiles/r1/sweeps.txt): 64 up to 256 K nodes, 48 up to 2 M, 32 above.
+static bool dense_enabled() {
+  const char* e = getenv("PPRB200_DENSE");
+  return !e || atoi(e) != 0;
+}
+
 static int default_mid_deg(int32_t n) {
   if (const char* e = getenv("PPRB200_MID_DEG")) return std::min(PAR_MID_MAX, std::max(1, atoi(e)));
+  // merge_dense_kernel: the 512-thread instantiation (two CTAs per SM) up to 128 successors
+  if (dense_enabled()) return PAR_MID_MAX;
   return n <= (1 << 18) ? 64 : (n <= (1 << 21) ? 48 : 32);
 }
 
@@ -503,6 +521,7 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
         if (owner_of_pos[(size_t)p] != rank) continue;  // multi-GPU: somebody else's node
         const long long d = row_off[(size_t)p + 1] - row_off[p];
         if (d > s->max_deg_par) s->max_deg_par = (int32_t)std::min<long long>(d, INT32_MAX);
+        if (cls == 2 && d > s->chunk) s->hub_items[c] += (int)((d + s->chunk - 1) / s->chunk);
         for (long long o = 0; o < d; o += s->chunk) {
           item_pos.push_back(p);
           item_off.push_back(row_off[p] + o);
@@ -564,7 +583,9 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   }
 
   const double t1 = now_ms();
-  const int Lp = roundup4((int)max_L);
+  // a basket never holds more than n keys: slots are sized for min(max_L, n) (runs clamp L the same way), so that the
+  // reference's grank(graph, graph.size(), 2 * graph.size(), ...) pattern (test/grankTest.cc:261-283) costs nothing extra
+  const int Lp = roundup4((int)effective_L(max_L, n));
   s->buf_bytes = (size_t)std::max(M, 1) * slot_bytes(Lp);
   if ((rc = dev_alloc(&s->d_row_off, (size_t)M + 1)) || (rc = dev_alloc(&s->d_col, (size_t)E)) ||
       (rc = dev_alloc(&s->d_label, (size_t)M)) || (rc = dev_alloc(&s->d_pos_of, (size_t)n)) || (rc = dev_alloc(&s->d_dense_of, (size_t)n)) ||
@@ -597,7 +618,7 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   if (s->n_items > 0) {
     // global-table pool of the order-free path: one table per CTA that can be in flight, sized for the worst case of
     // its class (big: the largest hub; mid: out-degree <= mid_deg) so that an acquired table can never overflow
-    const int Lpm = roundup4((int)max_L);
+    const int Lpm = Lp;
     auto pow2cap = [&](unsigned long long deg) {
       const unsigned long long worst = std::min<unsigned long long>(2ull * (deg * Lpm + 2ull), 2ull * ((unsigned long long)n + 1ull));
       unsigned int cap = 1024;
@@ -618,7 +639,8 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
     if ((rc = dev_alloc(&s->d_item_pos, (size_t)s->n_items)) || (rc = dev_alloc(&s->d_item_off, (size_t)s->n_items)) ||
         (rc = dev_alloc(&s->d_item_len, (size_t)s->n_items)) || (rc = dev_alloc(&s->d_pool, pool_bytes)) ||
         (rc = dev_alloc(&s->d_tbl_inuse, (size_t)n_tables)) || (rc = dev_alloc(&s->d_tbl_count, (size_t)n_tables)) ||
-        (rc = dev_alloc(&s->d_node_tbl, (size_t)M)) || (rc = dev_alloc(&s->d_node_done, (size_t)M))) {
+        (rc = dev_alloc(&s->d_node_tbl, (size_t)M)) || (rc = dev_alloc(&s->d_node_done, (size_t)M)) ||
+        (rc = dev_alloc(&s->d_fb_queue, (size_t)s->n_items))) {
       session_free(s);
       return rc;
     }
@@ -651,6 +673,8 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
   s->cur = s->stream;
   if (const char* e = getenv("PPRB200_OVERLAP")) s->overlap = atoi(e) != 0;
+  s->use_dense = dense_enabled();
+  if (const char* e = getenv("PPRB200_DENSE_THREADS")) s->dense_threads = atoi(e) == 512 ? 512 : 1024;
   if (getenv("PPRB200_PROF")) {
     if ((rc = dev_alloc(&s->d_prof, (size_t)2 * s->sm_count * 8 * 8))) { session_free(s); return rc; }
     cudaMemsetAsync(s->d_prof, 0, (size_t)2 * s->sm_count * 8 * 8 * sizeof(unsigned long long), st);
@@ -769,8 +793,27 @@ static cudaError_t launch_par(pprb200_session* s, const ParParams& P, int grid) 
   return cudaGetLastError();
 }
 
-// Enqueue the order-free path for the nodes of colour c above the hub threshold: hub chunks / big nodes on
-// 512-thread CTAs (1 per SM), mid-degree nodes on 128-thread CTAs (3 per SM).
+template <int H, int R, int TCAP, int CMAX, int COLCAP, int THREADS, int MINB>
+static cudaError_t launch_dense(pprb200_session* s, const DenseParams& P, int grid) {
+  const size_t smem = dense_smem_bytes<H, R, TCAP, CMAX, COLCAP>();
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(merge_dense_kernel<H, R, TCAP, CMAX, COLCAP, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured[dev & 63] = true;
+  }
+  merge_dense_kernel<H, R, TCAP, CMAX, COLCAP, THREADS, MINB><<<grid, THREADS, smem, s->cur>>>(P);
+  s->launch_count++;
+  return cudaGetLastError();
+}
+
+// Enqueue the order-free path for the nodes of colour c above the hub threshold.
+//   init (grank.h:64-83): merge_par_kernel on both classes (multiplicities, one pass over the column words).
+//   iterations / MC combine rounds: merge_dense_kernel -- 1024-thread CTAs (1 per SM, H = 8192, R = 16384) for the big
+//   class, 512-thread CTAs (2 per SM, H = 4096, R = 8192) for the mid class -- with merge_par_kernel behind it for the chunks of split
+//   hubs (launched alongside) and for whatever the dense kernels hand over through the device queue (launched after).
 static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
   ParParams P;
   std::memset(&P, 0, sizeof(P));
@@ -784,26 +827,79 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
   P.n_ids = s->n;
   P.use_sketch = 1;  // two-pass merge for single-item nodes of the big class (PPRB200_SKETCH=0: single pass, for A/B runs)
   if (const char* e = getenv("PPRB200_SKETCH")) P.use_sketch = atoi(e) != 0;
-  for (int cls = 1; cls >= 0; cls--) {
-    const int b = s->item_begin[c][cls], e = s->item_end[c][cls];
-    if (e == b) continue;
-    P.item_pos = s->d_item_pos + b;
-    P.item_begin = s->d_item_off + b;
-    P.item_len = s->d_item_len + b;
-    P.n_items = e - b;
-    P.work_idx = 6 + cls;  // (0..4: the exact-order cascade)
+  const bool dense = s->use_dense && !M.init_mode;
+  auto par_class = [&](int cls) {  // pool tables of a class
     P.pool = s->d_pool + s->pool_off[cls];
     P.capmax = s->tbl_cap[cls];
     P.tbl_bytes = (size_t)s->tbl_cap[cls] * (sizeof(GSlot) + sizeof(unsigned int) + 4 + 2);
     P.n_tables = s->tbl_count_cls[cls];
     P.tbl_inuse = s->d_tbl_inuse + s->tbl_first[cls];
     P.tbl_count = s->d_tbl_count + s->tbl_first[cls];
-    P.prof = s->d_prof ? s->d_prof + (size_t)cls * s->sm_count * 8 * 8 : nullptr;
-    s->cur = (s->overlap && cls == 0) ? s->aux[0] : s->stream;
-    cudaError_t err = cls == 1 ? launch_par<8192, 2048, 3072, PAR_CHUNK_MAX, 8192, 512>(s, P, std::min(s->sm_count, e - b))
-                               : launch_par<2048, 2048, 2048, PAR_MID_MAX, 0, 128>(s, P, std::min(s->sm_count * 3, e - b));
-    if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_par launch failed: %s", cudaGetErrorString(err));
+  };
+  cudaStream_t side = s->overlap ? s->aux[0] : s->stream;
+  for (int cls = 1; cls >= 0; cls--) {
+    const int b = s->item_begin[c][cls], e = s->item_end[c][cls];
+    if (e == b) continue;
+    const int n_hub = (dense && cls == 1) ? std::min(s->hub_items[c], e - b) : 0;
+    if (!dense || n_hub > 0) {
+      const int nb = dense ? n_hub : e - b;
+      P.item_pos = s->d_item_pos + b;
+      P.item_begin = s->d_item_off + b;
+      P.item_len = s->d_item_len + b;
+      P.n_items = nb;
+      P.item_queue = nullptr;
+      P.work_idx = 6 + cls;  // (0..4: the exact-order cascade)
+      par_class(cls);
+      P.prof = (s->d_prof && !dense) ? s->d_prof + (size_t)cls * s->sm_count * 8 * 8 : nullptr;
+      s->cur = (dense || cls == 0) ? side : s->stream;
+      cudaError_t err = cls == 1 ? launch_par<8192, 2048, 3072, PAR_CHUNK_MAX, 8192, 512>(s, P, std::min(s->sm_count, nb))
+                                 : launch_par<2048, 2048, 2048, PAR_MID_MAX, 0, 128>(s, P, std::min(s->sm_count * 3, nb));
+      if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_par launch failed: %s", cudaGetErrorString(err));
+    }
+    if (dense && e - b > n_hub) {
+      DenseParams D;
+      std::memset(&D, 0, sizeof(D));
+      D.M = P.M;
+      D.item_pos = s->d_item_pos + b + n_hub;
+      D.item_begin = s->d_item_off + b + n_hub;
+      D.item_len = s->d_item_len + b + n_hub;
+      D.n_items = e - b - n_hub;
+      D.item_base = b + n_hub;
+      D.chunk = s->chunk;
+      D.work_idx = 8 + cls;
+      D.fb_queue = s->d_fb_queue;
+      D.fb_idx = 4;
+      D.prof = s->d_prof ? s->d_prof + (size_t)cls * s->sm_count * 8 * 8 : nullptr;
+      s->cur = cls == 0 ? side : s->stream;
+      cudaError_t err;
+      if (cls == 1)
+        err = s->dense_threads == 512 ? launch_dense<8192, 16384, 2048, 2048, 1024, 512, 1>(s, D, std::min(s->sm_count, D.n_items))
+                                      : launch_dense<8192, 16384, 2048, 2048, 1024, 1024, 1>(s, D, std::min(s->sm_count, D.n_items));
+      else
+        err = launch_dense<4096, 8192, 2048, 1024, PAR_MID_MAX, 512, 2>(s, D, std::min(s->sm_count * 2, D.n_items));
+      if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_dense launch failed: %s", cudaGetErrorString(err));
+    }
   }
+  if (dense && s->item_end[c][1] > s->item_begin[c][0]) {
+    // whatever the dense kernels handed over (in practice a few nodes of the first iterations): merge_par from the queue
+    if (s->overlap) {
+      cudaEventRecord(s->ev_join[0], side);
+      cudaStreamWaitEvent(s->stream, s->ev_join[0], 0);
+    }
+    P.item_pos = s->d_item_pos;
+    P.item_begin = s->d_item_off;
+    P.item_len = s->d_item_len;
+    P.n_items = 0;
+    P.item_queue = s->d_fb_queue;
+    P.queue_idx = 4;
+    P.work_idx = 10;
+    par_class(1);
+    P.prof = nullptr;
+    s->cur = s->stream;
+    cudaError_t err = launch_par<8192, 2048, 3072, PAR_CHUNK_MAX, 8192, 512>(s, P, s->sm_count);
+    if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_par (hand-over queue) launch failed: %s", cudaGetErrorString(err));
+  }
+  s->cur = s->stream;
   return PPRB200_OK;
 }
 
@@ -877,7 +973,8 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
   int rc = check_params(K, L, iterations, damping);
   if (rc) return rc;
   if (L > s->max_L) return fail(PPRB200_ERR_PARAM, "L=%u exceeds the session's max_L=%u", L, s->max_L);
-  if ((size_t)roundup4((int)L) * 12 > 200 * 1024) return fail(PPRB200_ERR_PARAM, "L=%u is above this build's limit of 17064", L);
+  L = effective_L(L, s->n);
+  if ((size_t)roundup4((int)L) * 12 > 200 * 1024) return fail(PPRB200_ERR_PARAM, "min(L, n)=%u is above this build's limit of 17064", L);
   g_alloc_stream = s->stream;
   if ((rc = ensure_outputs(s, K))) return rc;
   if (s->world > 1 && !s->attached) return fail(PPRB200_ERR_STATE, "world=%d session: call pprb200_session_ipc_attach before running", s->world);
@@ -971,7 +1068,8 @@ static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t 
   int rc = check_params(K, L, R, damping);
   if (rc) return rc;
   if (L > s->max_L) return fail(PPRB200_ERR_PARAM, "L=%u exceeds the session's max_L=%u", L, s->max_L);
-  if ((size_t)roundup4((int)L) * 12 > 200 * 1024) return fail(PPRB200_ERR_PARAM, "L=%u is above this build's limit of 17064", L);
+  L = effective_L(L, s->n);
+  if ((size_t)roundup4((int)L) * 12 > 200 * 1024) return fail(PPRB200_ERR_PARAM, "min(L, n)=%u is above this build's limit of 17064", L);
   g_alloc_stream = s->stream;
   if ((rc = ensure_outputs(s, K))) return rc;
   if (s->world > 1 && !s->attached) return fail(PPRB200_ERR_STATE, "world=%d session: call pprb200_session_ipc_attach before running", s->world);
@@ -1096,6 +1194,7 @@ static int session_stats_impl(pprb200_session* s, pprb200_stats* out) {
   unsigned long long fin[2];
   CUDA_TRY(cudaMemcpy(&h, s->d_state, sizeof(h), cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(fin, s->d_final_stats, sizeof(fin), cudaMemcpyDeviceToHost));
+  if (h.peer_timeout) return fail(PPRB200_ERR_CUDA, "peer barrier timed out: a rank of this %d-GPU run died or never attached; results are invalid", s->world);
   out->iterations_run = (uint32_t)h.iter;
   out->n_gpus = (uint32_t)s->world;
   uint64_t ni = 0;
@@ -1128,6 +1227,11 @@ static int session_stats_impl(pprb200_session* s, pprb200_stats* out) {
 static int session_fetch_impl(pprb200_session* s, int32_t* out_ids, double* out_scores, uint32_t* out_cnt) {
   if (s->last_mode < 0) return fail(PPRB200_ERR_STATE, "no run has been enqueued on this session");
   CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (s->world > 1) {
+    int timed_out = 0;
+    CUDA_TRY(cudaMemcpy(&timed_out, reinterpret_cast<const unsigned char*>(s->d_state) + offsetof(RunState, peer_timeout), sizeof(int), cudaMemcpyDeviceToHost));
+    if (timed_out) return fail(PPRB200_ERR_CUDA, "peer barrier timed out: a rank of this %d-GPU run died or never attached; results are invalid", s->world);
+  }
   const size_t cnt = (size_t)s->n * s->last_K;
   if (out_ids && cnt) CUDA_TRY(cudaMemcpyAsync(out_ids, s->d_out_ids, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
   if (out_scores && cnt) CUDA_TRY(cudaMemcpyAsync(out_scores, s->d_out_scores, cnt * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -1229,11 +1333,19 @@ int pprb200_debug_prof(pprb200_session* s, unsigned long long* out, int* n_ctas)
   return PPRB200_OK;
 }
 
+// SM clocks a cross-GPU barrier waits before it declares a peer dead (PPRB200_PEER_TIMEOUT_MS, default 30 s at ~2 GHz)
+static long long peer_timeout_cycles() {
+  double ms = 30000.0;
+  if (const char* e = getenv("PPRB200_PEER_TIMEOUT_MS")) ms = std::max(1.0, atof(e));
+  return (long long)(ms * 2.0e6);
+}
+
 // ---- multi-GPU wiring: CUDA IPC handles of the two basket buffers and the mailbox ----------------------------------
 int pprb200_session_ipc_export(pprb200_session* s, void* out) {
   if (!s || !out) return fail(PPRB200_ERR_PARAM, "NULL argument");
   std::lock_guard<std::mutex> lk(g_api_mutex);
   cudaIpcMemHandle_t h[3];
+  CUDA_TRY(cudaStreamSynchronize(s->stream));  // the mailbox is zeroed before any peer can post into it
   CUDA_TRY(cudaIpcGetMemHandle(&h[0], s->d_buf[0]));
   CUDA_TRY(cudaIpcGetMemHandle(&h[1], s->d_buf[1]));
   CUDA_TRY(cudaIpcGetMemHandle(&h[2], s->d_mbox));
@@ -1250,6 +1362,7 @@ int pprb200_session_ipc_attach(pprb200_session* s, const void* all_handles) {
   std::memset(&pd, 0, sizeof(pd));
   pd.world = s->world;
   pd.rank = s->rank;
+  pd.timeout_cycles = peer_timeout_cycles();
   for (int r = 0; r < s->world; r++) {
     if (r == s->rank) {
       pd.buf[r][0] = s->d_buf[0]; pd.buf[r][1] = s->d_buf[1]; pd.mbox[r] = s->d_mbox;
