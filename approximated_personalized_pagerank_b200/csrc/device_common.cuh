@@ -47,6 +47,9 @@ struct RunState {
   unsigned int ws_next;      // bump allocator for the global-table workspace
   int peer_timeout;          // set when a cross-GPU barrier gave up waiting
   unsigned long long barrier_seq;  // executed cross-GPU barriers (kept across runs)
+  // merge_dense_kernel bookkeeping (pprb200_debug_counters): nodes finished, nodes that ran pass 2, nodes with tau = 0,
+  // hand-overs by reason (untrusted contribution, candidates > CMAX, tail table full), split-hub items passed on
+  unsigned long long dbg[8];
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -43,7 +43,10 @@ struct WalkParams {
   int queue_out_idx;
   unsigned long long* ws;     // fallback: gridDim.x x (table of tcap 64-bit slots + first-touch list of tcap 32-bit slot indices)
   PeerDev peers;              // multi-GPU: source index i of this rank maps to position src_begin + i*world + rank
+  const unsigned long long* rowdeg;  // [M] packed row word: first column offset << ROWDEG_SHIFT | out-degree (one 8-byte gather per hop)
 };
+
+constexpr int ROWDEG_SHIFT = 26;  // out-degree < 2^26, column offsets < 2^38 (validated when the session is created)
 
 struct WalkSlot {
   uint32_t key;
@@ -133,43 +136,63 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : 3)) mc_walk_ker
     __syncthreads();
 
     // ---- walks ----
+    // Every lane carries one walk; the warp advances all of them in lock step, two hops per iteration (one Philox block
+    // yields the successor choice and the teleport coin of an even and an odd hop), and lanes whose walk has ended are
+    // refilled at the top of the next iteration with one shared-memory atomic per warp. The round-1 loop let every thread
+    // run its own walk-fetch / Philox / probe sequence: 12.6 of 32 lanes active per issued instruction (profiles/r1).
     unsigned long long steps = 0;
-    for (;;) {
-      const unsigned int w = atomicAdd(&S->next_walk, 1u);
-      if ((unsigned long long)w >= P.W) break;
-      if (*reinterpret_cast<volatile int*>(&S->overflow)) break;
-      uint32_t pos = (uint32_t)p;
-      uint32_t rnd[4];
-      for (unsigned int step = 0; step < MC_MAX_STEPS; step++) {
-        const long long rb = P.g.row_off[pos], re = P.g.row_off[pos + 1];
-        if ((step & 1u) == 0u)
-          philox4x32_10(step >> 1, 0u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), src_dense, w, rnd);
-        const uint32_t a = rnd[(step & 1u) * 2u], c = rnd[(step & 1u) * 2u + 1u];
-        const unsigned long long deg = (unsigned long long)(re - rb);
-        const uint32_t word = P.g.col[rb + (long long)(((unsigned long long)a * deg) >> 32)];  // :149, random successor
-        // count the visit (:152-153 without the cap)
-        unsigned int h = slot0(word);
-        for (;;) {
-          const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&tbl[h].key);
-          if (cur == word) break;
-          if (cur == WALK_EMPTY) {
-            const uint32_t old = atomicCAS(&tbl[h].key, WALK_EMPTY, word);
-            if (old == WALK_EMPTY) {
-              const unsigned int pos = atomicAdd(&S->ndistinct, 1u);
-              list_set(pos, h);
-              if (pos + 1u > P.limit) S->overflow = 1;
-              break;
-            }
-            if (old == word) break;
+    {
+      const int lane = tid & 31;
+      bool active = false;
+      uint32_t pos = (uint32_t)p, w = 0u;
+      unsigned int step = 0u;
+      for (;;) {
+        const unsigned need = __ballot_sync(FULL, !active);
+        if (need) {
+          unsigned int base = 0u;
+          const int leader = __ffs(need) - 1;
+          if (lane == leader) base = atomicAdd(&S->next_walk, (unsigned int)__popc(need));
+          base = __shfl_sync(FULL, base, leader);
+          if (!active) {
+            w = base + (unsigned int)__popc(need & ((1u << lane) - 1u));
+            if ((unsigned long long)w < P.W && !*reinterpret_cast<volatile int*>(&S->overflow)) { active = true; pos = (uint32_t)p; step = 0u; }
           }
-          h = h + 1u == cap ? 0u : h + 1u;
         }
-        atomicAdd(&tbl[h].count, 1u);
-        steps++;
-        if (word & COL_SINK) break;   // :144-145 the walk stops on reaching a sink
-        if (!(c < P.thresh)) break;   // :155
-        if (*reinterpret_cast<volatile int*>(&S->overflow)) break;
-        pos = word & COL_POS_MASK;
+        if (!__any_sync(FULL, active)) break;
+        uint32_t rnd[4];
+        philox4x32_10(step >> 1, 0u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), src_dense, w, rnd);  // (step is even here)
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          if (active) {
+            const unsigned long long rw = __ldg(P.rowdeg + pos);
+            const unsigned long long deg = rw & ((1ull << ROWDEG_SHIFT) - 1ull);
+            const uint32_t a = rnd[2 * half], c = rnd[2 * half + 1];
+            const uint32_t word = __ldg(P.g.col + (rw >> ROWDEG_SHIFT) + (((unsigned long long)a * deg) >> 32));  // :149, random successor
+            // count the visit (:152-153 without the cap)
+            unsigned int h = slot0(word);
+            for (;;) {
+              const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&tbl[h].key);
+              if (cur == word) break;
+              if (cur == WALK_EMPTY) {
+                const uint32_t old = atomicCAS(&tbl[h].key, WALK_EMPTY, word);
+                if (old == WALK_EMPTY) {
+                  const unsigned int np = atomicAdd(&S->ndistinct, 1u);
+                  list_set(np, h);
+                  if (np + 1u > P.limit) S->overflow = 1;
+                  break;
+                }
+                if (old == word) break;
+              }
+              h = h + 1u == cap ? 0u : h + 1u;
+            }
+            atomicAdd(&tbl[h].count, 1u);
+            steps++;
+            step++;
+            // :144-145 the walk stops on reaching a sink; :155 the teleport coin; hard cap; a full table ends the source
+            if ((word & COL_SINK) || !(c < P.thresh) || step >= MC_MAX_STEPS || *reinterpret_cast<volatile int*>(&S->overflow)) active = false;
+            else pos = word & COL_POS_MASK;
+          }
+        }
       }
     }
     __syncthreads();

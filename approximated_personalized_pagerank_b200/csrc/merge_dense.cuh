@@ -46,7 +46,9 @@ struct DenseShared {
   ParShared P;   // scratch of the block reductions / radix select
   int ncol;      // non-sink column words staged for the current tile
   int bail;      // hand the node to the general kernel
-  int lvl[2];    // exact candidates >= theta0 / >= 0.75 theta0
+  int lvl[4];    // exact candidates >= theta0, 3/4 theta0, 1/2 theta0, 1/16 theta0
+  unsigned long long cut_bits;  // rank-count select: the L-th largest score,
+  int cut_gt, cut_eq;           //   candidates above it / equal to it
 };
 
 template <int H, int R, int TCAP, int CMAX, int COLCAP>
@@ -163,13 +165,14 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
     }
   };
 
+  unsigned long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // (thread 0)
   unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long t_last = clock64();
 #define DPROF_MARK(i) do { if (P.prof && tid == 0) { const long long t_now = clock64(); pc[i] += (unsigned long long)(t_now - t_last); t_last = t_now; } } while (0)
 
   for (;;) {
     __syncthreads();
-    if (tid == 0) { S->item = atomicAdd(&st->work[P.work_idx], 1u); DS->bail = 0; S->ncand = 0; DS->lvl[0] = 0; DS->lvl[1] = 0; }
+    if (tid == 0) { S->item = atomicAdd(&st->work[P.work_idx], 1u); DS->bail = 0; S->ncand = 0; DS->lvl[0] = DS->lvl[1] = DS->lvl[2] = DS->lvl[3] = 0; }
     __syncthreads();
     const unsigned int item = S->item;
     if (item >= (unsigned)P.n_items) break;
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
     const int clen = P.item_len[item];
     const long long deg = M.g.row_off[p + 1] - M.g.row_off[p];
     if (deg > (long long)P.chunk) {  // a chunk of a split hub: the general kernel's job
-      if (tid == 0) P.fb_queue[atomicAdd(&st->qcount[P.fb_idx], 1u)] = (unsigned int)P.item_base + item;
+      if (tid == 0) { P.fb_queue[atomicAdd(&st->qcount[P.fb_idx], 1u)] = (unsigned int)P.item_base + item; dbg[6]++; }
       continue;
     }
     const int self_id = M.g.label[p];
@@ -344,68 +347,67 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
     sweep(1);
     DPROF_MARK(1);
     bool bail = __syncthreads_or(bad ? 1 : 0) != 0;  // (also: pass 1 complete)
+    dbg[3] += bail;
 
-    // ---- exact candidates (dense + pre labels) that reach the bound -> compact (score bits, label) arrays ----
-    // compacted from thb = theta0 / 2 up; tau = the highest of (theta0, 3/4 theta0, theta0 / 2) that L of them reach
+    // ---- exact candidates (dense + pre labels) -> compact (score bits, label) arrays ----
+    // scan 1 counts how many reach theta0, 3/4, 1/2, 1/16 of it: tau = the highest level that L of them reach is a lower
+    // bound of the cut (0 when none is); scan 2 compacts the candidates >= tau.
     bool dropped_local = false;  // this thread saw a candidate that is not in the compact arrays
-    double th = theta0 * 0.5;
-    double tau = th;
+    double tau = 0.0;
     int n = 0;
     if (!bail) {
-      for (int attempt = 0;; attempt++) {
-        dropped_local = false;
-        const unsigned long long thb = (unsigned long long)__double_as_longlong(th);
-        const unsigned long long la = (unsigned long long)__double_as_longlong(theta0), lb = (unsigned long long)__double_as_longlong(theta0 * 0.75);
-        int ca = 0, cq = 0;
-        for (int i0 = 0; i0 < H; i0 += THREADS) {
-          const int i = i0 + tid;
-          const uint2 a = i < H ? acc[i] : make_uint2(0u, 0u);
-          const bool nz = (a.x | a.y) != 0u;
-          const unsigned long long bits = (unsigned long long)__double_as_longlong(word_score(a));
-          const bool ok = nz && bits >= thb;
-          dropped_local |= nz && !ok;
-          ca += ok && bits >= la;
-          cq += ok && bits >= lb;
-          append(ok, bits, i);
-        }
-        for (int i0 = 0; i0 < npre; i0 += THREADS) {
-          const int i = i0 + tid;
-          bool ok = false;
-          unsigned long long bits = 0ull;
-          int id = 0;
-          if (i < npre) {
-            const int sl = t_list[i];
-            const uint2 a = t_acc[sl];
-            id = ~t_keys[sl];
-            const bool nz = (a.x | a.y) != 0u;
-            bits = (unsigned long long)__double_as_longlong(word_score(a));
-            ok = nz && bits >= thb;
-            dropped_local |= nz && !ok;
-            ca += ok && bits >= la;
-            cq += ok && bits >= lb;
-          }
-          append(ok, bits, id);
-        }
-        if (attempt == 0 && theta0 > 0.0) {
-          ca = warp_sum_int(ca);
-          cq = warp_sum_int(cq);
-          if (lane == 0) { if (ca) atomicAdd(&DS->lvl[0], ca); if (cq) atomicAdd(&DS->lvl[1], cq); }
+      if (theta0 > 0.0) {
+        const unsigned long long l0 = (unsigned long long)__double_as_longlong(theta0), l1 = (unsigned long long)__double_as_longlong(theta0 * 0.75),
+                                 l2 = (unsigned long long)__double_as_longlong(theta0 * 0.5), l3 = (unsigned long long)__double_as_longlong(theta0 * 0.0625);
+        int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        auto tally = [&](uint2 a) {
+          const unsigned long long bits = (unsigned long long)__double_as_longlong(word_score(a));  // (empty word: 0, below every level)
+          c0 += bits >= l0; c1 += bits >= l1; c2 += bits >= l2; c3 += bits >= l3;
+        };
+        for (int i = tid; i < H; i += THREADS) tally(acc[i]);
+        for (int i = tid; i < npre; i += THREADS) tally(t_acc[t_list[i]]);
+        c0 = warp_sum_int(c0); c1 = warp_sum_int(c1); c2 = warp_sum_int(c2); c3 = warp_sum_int(c3);
+        if (lane == 0) {
+          if (c0) atomicAdd(&DS->lvl[0], c0);
+          if (c1) atomicAdd(&DS->lvl[1], c1);
+          if (c2) atomicAdd(&DS->lvl[2], c2);
+          if (c3) atomicAdd(&DS->lvl[3], c3);
         }
         __syncthreads();
-        n = S->ncand;
-        tau = th;
-        if (n >= L || th == 0.0) {
-          if (attempt == 0 && theta0 > 0.0) tau = DS->lvl[0] >= L ? theta0 : (DS->lvl[1] >= L ? theta0 * 0.75 : th);
-          break;
-        }
-        __syncthreads();
-        if (tid == 0) S->ncand = 0;  // fewer than L candidates reach the bound: it is none -- relax it and compact again
-        __syncthreads();
-        th = attempt == 0 ? th * 0.125 : 0.0;
+        tau = DS->lvl[0] >= L ? theta0 : (DS->lvl[1] >= L ? theta0 * 0.75 : (DS->lvl[2] >= L ? theta0 * 0.5 : (DS->lvl[3] >= L ? theta0 * 0.0625 : 0.0)));
       }
-      if (n > CMAX) bail = true;
+      const unsigned long long tb0 = (unsigned long long)__double_as_longlong(tau);
+      for (int i0 = 0; i0 < H; i0 += THREADS) {
+        const int i = i0 + tid;
+        const uint2 a = i < H ? acc[i] : make_uint2(0u, 0u);
+        const bool nz = (a.x | a.y) != 0u;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(word_score(a));
+        const bool ok = nz && bits >= tb0;
+        dropped_local |= nz && !ok;
+        append(ok, bits, i);
+      }
+      for (int i0 = 0; i0 < npre; i0 += THREADS) {
+        const int i = i0 + tid;
+        bool ok = false;
+        unsigned long long bits = 0ull;
+        int id = 0;
+        if (i < npre) {
+          const int sl = t_list[i];
+          const uint2 a = t_acc[sl];
+          id = ~t_keys[sl];
+          const bool nz = (a.x | a.y) != 0u;
+          bits = (unsigned long long)__double_as_longlong(word_score(a));
+          ok = nz && bits >= tb0;
+          dropped_local |= nz && !ok;
+        }
+        append(ok, bits, id);
+      }
+      __syncthreads();
+      n = S->ncand;
+      if (n > CMAX) { bail = true; dbg[4]++; }
+      dbg[2] += tau == 0.0;
     }
-    const unsigned long long thb = (unsigned long long)__double_as_longlong(th);  // what the compact arrays were filtered with
+    const unsigned long long thb = (unsigned long long)__double_as_longlong(tau);  // what the compact arrays were filtered with
     DPROF_MARK(2);
 
     // ---- sketch buckets that can hold a kept label: upper bound >= tau (tau > 0 only with >= L candidates above it) ----
@@ -422,10 +424,13 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
       }
       any = __syncthreads_or(any);
       DPROF_MARK(3);
+      dbg[1] += any != 0;
       if (any) {
+        // (the node's own label is normally a pre label; if it lost its home slot its self term went to the sketch too)
+        if (tid == 0 && wanted(self_id) && !tail_add(self_id, xself)) S->spilled = 1;
         sweep(2);
         __syncthreads();
-        if (S->spilled) bail = true;
+        if (S->spilled) { bail = true; dbg[5]++; }
         if (!bail) {
           const int nt0 = S->tcount;
           for (int i0 = npre; i0 < nt0; i0 += THREADS) {
@@ -444,7 +449,7 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
           }
           __syncthreads();
           n = S->ncand;
-          if (n > CMAX) bail = true;
+          if (n > CMAX) { bail = true; dbg[4]++; }
         }
       }
       DPROF_MARK(4);
@@ -467,7 +472,25 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
         int krem;
         auto keyfn = [&](int i) { return kb[i]; };
         int ntied = 0;
-        thr.bits = block_radix_select(n, L, keyfn, all, S, &tie, &krem, &ntied);
+        if (n * n <= 256 * THREADS) {
+          // few candidates (the filter leaves little more than L): every thread ranks its candidates against all of them --
+          // two barriers instead of the radix select's dozen. The value with (above < L <= above + equal) is the cut.
+          for (int i = tid; i < n; i += THREADS) {
+            const unsigned long long b = kb[i];
+            int gt = 0, eq = 0;
+#pragma unroll 4
+            for (int j = 0; j < n; j++) { const unsigned long long x = kb[j]; gt += x > b; eq += x == b; }
+            if (gt < L && gt + eq >= L) { DS->cut_bits = b; DS->cut_gt = gt; DS->cut_eq = eq; }  // (same values from every writer)
+          }
+          __syncthreads();
+          thr.bits = DS->cut_bits;
+          ntied = DS->cut_eq;
+          krem = L - DS->cut_gt;
+          tie = DS->cut_gt + DS->cut_eq > L;
+          __syncthreads();
+        } else {
+          thr.bits = block_radix_select(n, L, keyfn, all, S, &tie, &krem, &ntied);
+        }
         if (tie) {
           const unsigned long long tb = thr.bits;
           if (ntied <= 32) {
@@ -593,6 +616,8 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
     if (s_ties) atomicAdd(&st->ties, s_ties);
     if (s_bytes) atomicAdd(&st->abytes, s_bytes);
     if (s_requeue) atomicAdd(&st->requeues, s_requeue);
+    dbg[0] = s_nodes;
+    for (int i = 0; i < 8; i++) if (dbg[i]) atomicAdd(&st->dbg[i], dbg[i]);
   }
 }
 

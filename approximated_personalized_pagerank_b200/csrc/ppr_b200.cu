@@ -58,6 +58,16 @@ __global__ void pool_init_kernel(unsigned char* pool, size_t tbl_bytes, unsigned
   }
 }
 
+// debug: the device-side Philox4x32-10 on caller-chosen (counter, key) blocks (known-answer tests)
+__global__ void philox_probe_kernel(const uint32_t* ctr_key, uint32_t* out, int nblocks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nblocks) return;
+  const uint32_t* c = ctr_key + (size_t)i * 6;
+  uint32_t r[4];
+  philox4x32_10(c[0], c[1], c[2], c[3], c[4], c[5], r);
+  for (int j = 0; j < 4; j++) out[(size_t)i * 4 + j] = r[j];
+}
+
 // end of an init / combine phase: clear cascade counters (and optionally the work statistics)
 __global__ void phase_end_kernel(RunState* st, int clear_stats, int flip_both, PeerDev peers, int barrier) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -182,6 +192,8 @@ struct pprb200_session {
   int64_t E = 0;
   uint32_t max_L = 0, hub_threshold = 0;
   int rank = 0, world = 1;
+  int device = 0;                   // CUDA device the session lives on
+  bool ipc = false;                 // basket buffers / mailbox are plain cudaMalloc allocations (exported through CUDA IPC)
   PeerDev peers;                    // device view of the peer mappings (world 1: zeroed)
   int* d_seq_list = nullptr;        // world > 1: own positions of the exact-order class (range_begin/end index it)
   Mailbox* d_mbox = nullptr;        // [2][MAX_WORLD] barrier mailboxes of this rank, written by the peers
@@ -216,6 +228,7 @@ struct pprb200_session {
   int32_t max_deg = 0;
   // device
   long long* d_row_off = nullptr;
+  unsigned long long* d_rowdeg = nullptr;  // [M] offset << ROWDEG_SHIFT | out-degree (MC walk kernel)
   uint32_t* d_col = nullptr;
   int* d_label = nullptr;
   int* d_pos_of = nullptr;
@@ -264,14 +277,14 @@ static int device_ok() {
   }
   int dev = 0;
   cudaGetDevice(&dev);
-  static int checked_dev = -1;  // cudaGetDeviceProperties costs a millisecond or two: ask once per device
-  if (dev == checked_dev) return PPRB200_OK;
+  static bool checked[64] = {false};  // (attribute queries cost a millisecond or two: ask once per device)
+  if (checked[dev & 63]) return PPRB200_OK;
   int major = 0, minor = 0;
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
       cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess)
     return fail(PPRB200_ERR_CUDA, "cudaDeviceGetAttribute failed");
   if (major != 10) return fail(PPRB200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, major, minor);
-  checked_dev = dev;
+  checked[dev & 63] = true;
   return PPRB200_OK;
 }
 
@@ -282,17 +295,17 @@ static int device_ok() {
 static cudaStream_t g_alloc_stream = nullptr;
 
 static void pool_setup_once() {
-  static bool done = false;
-  if (done) return;
+  static bool done[64] = {false};  // per device
   int dev = 0;
   cudaGetDevice(&dev);
+  if (done[dev & 63]) return;
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
     unsigned long long keep = ~0ull;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
   cudaGetLastError();
-  done = true;
+  done[dev & 63] = true;
 }
 
 template <typename T>
@@ -316,10 +329,10 @@ static void session_free(pprb200_session* s) {
     for (int i = 0; i < 3; i++)
       if (s->ipc_opened[r][i]) cudaIpcCloseMemHandle(s->ipc_opened[r][i]);
   g_alloc_stream = s->stream;
-  const bool ipc = s->world > 1;
+  const bool ipc = s->ipc;
   dev_free(s->d_mbox, ipc);
   dev_free(s->d_buf[0], ipc); dev_free(s->d_buf[1], ipc);
-  void* plain[] = {s->d_seq_list, s->d_row_off, s->d_col, s->d_label, s->d_pos_of, s->d_dense_of, s->d_colour, s->d_queue[0], s->d_queue[1],
+  void* plain[] = {s->d_rowdeg, s->d_seq_list, s->d_row_off, s->d_col, s->d_label, s->d_pos_of, s->d_dense_of, s->d_colour, s->d_queue[0], s->d_queue[1],
                    s->d_queue[2], s->d_queue[3], s->d_ncand, s->d_state, s->d_final_stats, s->d_ws, s->d_out_ids, s->d_out_scores,
                    s->d_out_cnt, s->d_item_pos, s->d_item_off, s->d_item_len, s->d_pool, s->d_walk_ws, s->d_prof, s->d_tbl_inuse,
                    s->d_tbl_count, s->d_node_tbl, s->d_node_done, s->d_fb_queue};
@@ -355,6 +368,9 @@ static int default_mid_deg(int32_t n) {
 // becomes the tail of every iteration (R-MAT-22 on 8 GPUs: 99 M node-iterations/s with 4096, 92 M with 32768).
 static int default_chunk(int32_t n, int world) {
   if (const char* e = getenv("PPRB200_CHUNK")) return std::min(1 << 20, std::max(32, atoi(e)));
+  // one GPU, merge_dense_kernel: a whole hub on one CTA (the largest R-MAT-22 hub, 16 M entries, is ~8 ms of a >= 10 ms
+  // iteration) beats its chunks meeting in an L2-resident table by a wide margin (profiles/r2/launches_r22_v2.txt)
+  if (world <= 1 && dense_enabled()) return 1 << 20;
   int c = 2048;
   while (c < 32768 && (long long)c * 64 * std::max(world, 1) < (long long)n) c <<= 1;
   return c;
@@ -422,68 +438,63 @@ struct HostPlanOut {
   int32_t* summary;     // [16] M, n_items, chunk, mid_deg, range_begin[2], range_end[2], item_begin[2][2], item_end[2][2]
 };
 
-static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour_in,
-                               uint32_t max_L, uint32_t hub_threshold, int32_t rank, int32_t world, void* stream,
-                               pprb200_session** out, bool need_colour = true, const HostPlanOut* plan_out = nullptr) {
-  if (!out) return fail(PPRB200_ERR_PARAM, "out is NULL");
-  *out = nullptr;
-  if (max_L == 0) return fail(PPRB200_ERR_PARAM, "L must be positive");
-  if (world < 1 || world > MAX_WORLD || rank < 0 || rank >= world) return fail(PPRB200_ERR_PARAM, "rank %d / world %d: need 0 <= rank < world <= %d", rank, world, MAX_WORLD);
-  int rc = validate_csr(row_ptr, col, n);
-  if (rc) return rc;
-  if (!plan_out && (rc = device_ok())) return rc;
+// The host front half, split in two so that a multi-GPU run plans once:
+//   HostPlan  rank-independent: colouring, storage order (+ owner of every position), rank labels, CSR in storage order
+//   RankPlan  what one rank of `world` works on: its exact-order positions and its order-free work items
+struct HostPlan {
+  int32_t n = 0, M = 0;
+  int64_t E = 0;
+  int world = 1;
+  uint32_t hub_threshold = 0;
+  int chunk = 4096, mid_deg = 64;
+  int32_t colour_count[2] = {0, 0};
+  int32_t max_deg = 0, max_deg_seq = 0;
+  int cls_begin[2][3], cls_end[2][3];
+  std::vector<uint8_t> colour;
+  std::vector<int32_t> order, owner_of_pos, dense_of, rank_of, pos_of, label;
+  std::vector<long long> row_off;
+  std::vector<unsigned long long> rowdeg;
+  std::vector<uint32_t> enc;
+  double prep_ms = 0;
+};
 
+struct RankPlan {
+  int range_begin[2] = {0, 0}, range_end[2] = {0, 0};
+  std::vector<int> seq_list;  // world > 1: this rank's positions of the exact-order class, colour-major
+  int item_begin[2][2] = {{0, 0}, {0, 0}}, item_end[2][2] = {{0, 0}, {0, 0}};
+  int hub_items[2] = {0, 0};
+  int32_t max_deg_par = 0;
+  std::vector<int> item_pos;
+  std::vector<long long> item_off;
+  std::vector<int> item_len;
+};
+
+static int build_host_plan(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour_in, uint32_t hub_threshold,
+                           int32_t world, bool need_colour, HostPlan& H) {
   const double t0 = now_ms();
-  pprb200_session* s = new pprb200_session();
-  std::memset(&s->peers, 0, sizeof(s->peers));
-  std::memset(s->ipc_opened, 0, sizeof(s->ipc_opened));
-  if (!plan_out) pool_setup_once();
-  g_alloc_stream = (cudaStream_t)stream;
-  s->n = n;
-  s->max_L = max_L;
-  s->hub_threshold = hub_threshold == 0 ? PPRB200_DEFAULT_HUB_THRESHOLD : hub_threshold;
-  s->rank = rank;
-  s->world = world;
-  s->stream = (cudaStream_t)stream;
-  if (!plan_out) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
-
-  std::vector<uint8_t> colour((size_t)n);
+  int rc;
+  H.n = n;
+  H.world = world;
+  H.hub_threshold = hub_threshold == 0 ? PPRB200_DEFAULT_HUB_THRESHOLD : hub_threshold;
+  H.colour.assign((size_t)n, 0);
+  std::vector<uint8_t>& colour = H.colour;
   if (colour_in) std::memcpy(colour.data(), colour_in, (size_t)n);
-  else if (!need_colour) std::fill(colour.begin(), colour.end(), (uint8_t)0);  // MC-only session: one class
-  else if ((rc = find_partitions(row_ptr, col, n, colour.data()))) { delete s; return rc; }
+  else if (need_colour && (rc = find_partitions(row_ptr, col, n, colour.data()))) return rc;  // (MC-only session: one class)
   for (int32_t v = 0; v < n; v++) {
-    if (colour[v] > 1) { delete s; return fail(PPRB200_ERR_PARAM, "colour[%d] = %d is not 0/1", v, colour[v]); }
-    s->colour_count[colour[v]]++;
+    if (colour[v] > 1) return fail(PPRB200_ERR_PARAM, "colour[%d] = %d is not 0/1", v, colour[v]);
+    H.colour_count[colour[v]]++;
   }
-
   const double t_col = now_ms();
   // storage order: colour-major; inside a colour the exact-order class first, then the order-free class
   // (mid, big); every class by out-degree descending (ties by dense id) -- big nodes first for load balance
-  s->chunk = default_chunk(n, world);
-  s->mid_deg = default_mid_deg(n);
-  std::vector<int32_t> order;
-  int cls_begin[2][3], cls_end[2][3];
-  std::vector<int32_t> owner_of_pos;
-  storage_order(row_ptr, n, colour.data(), s->hub_threshold, s->mid_deg, order, cls_begin, cls_end, world, &owner_of_pos);
-  std::vector<int> seq_list;  // world > 1: this rank's positions of the exact-order class, colour-major
-  for (int c = 0; c < 2; c++) {
-    if (world == 1) {
-      s->range_begin[c] = cls_begin[c][0];
-      s->range_end[c] = cls_end[c][0];
-    } else {
-      s->range_begin[c] = (int)seq_list.size();
-      for (int p = cls_begin[c][0]; p < cls_end[c][0]; p++)
-        if (owner_of_pos[(size_t)p] == rank) seq_list.push_back(p);
-      s->range_end[c] = (int)seq_list.size();
-    }
-  }
+  H.chunk = default_chunk(n, world);
+  H.mid_deg = default_mid_deg(n);
+  storage_order(row_ptr, n, colour.data(), H.hub_threshold, H.mid_deg, H.order, H.cls_begin, H.cls_end, world, &H.owner_of_pos);
+  const std::vector<int32_t>& order = H.order;
   const double t_ord = now_ms();
   // rank labels: in-degree descending, ties by dense id (the keys stored in the baskets) -- a counting sort
-  std::vector<int32_t> dense_of((size_t)n), rank_of((size_t)n);
+  H.dense_of.assign((size_t)n, 0);
+  H.rank_of.assign((size_t)n, 0);
   {
     std::vector<uint32_t> indeg((size_t)n);
     host_indegree(col, row_ptr[n], n, indeg.data());
@@ -494,103 +505,133 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
     for (size_t i = 0; i <= (size_t)max_in; i++) start[i + 1] += start[i];
     for (int32_t v = 0; v < n; v++) {
       const int32_t r = start[(size_t)(max_in - indeg[(size_t)v])]++;
-      dense_of[(size_t)r] = v;
-      rank_of[(size_t)v] = r;
+      H.dense_of[(size_t)r] = v;
+      H.rank_of[(size_t)v] = r;
     }
   }
   const double t_rank = now_ms();
   const int32_t M = (int32_t)order.size();
-  s->M = M;
-  std::vector<int32_t> pos_of((size_t)n, -1);
-  for (int32_t p = 0; p < M; p++) pos_of[order[p]] = p;
-  std::vector<long long> row_off((size_t)M + 1, 0);
+  H.M = M;
+  H.pos_of.assign((size_t)n, -1);
+  for (int32_t p = 0; p < M; p++) H.pos_of[order[p]] = p;
+  H.row_off.assign((size_t)M + 1, 0);
+  H.rowdeg.assign((size_t)std::max(M, 1), 0ull);
+  H.label.assign((size_t)std::max(M, 1), 0);
   for (int32_t p = 0; p < M; p++) {
     const int64_t d = row_ptr[order[p] + 1] - row_ptr[order[p]];
-    row_off[(size_t)p + 1] = row_off[p] + d;
-    if (d > s->max_deg) s->max_deg = (int32_t)std::min<int64_t>(d, INT32_MAX);
+    H.row_off[(size_t)p + 1] = H.row_off[p] + d;
+    if (d > H.max_deg) H.max_deg = (int32_t)std::min<int64_t>(d, INT32_MAX);
+    if ((unsigned long long)d >> ROWDEG_SHIFT || (unsigned long long)H.row_off[p] >> (64 - ROWDEG_SHIFT))
+      return fail(PPRB200_ERR_GRAPH, "out-degree %lld / edge offset %lld exceed the packed row word (2^%d successors per node, 2^%d edges)",
+                  (long long)d, H.row_off[p], ROWDEG_SHIFT, 64 - ROWDEG_SHIFT);
+    H.rowdeg[(size_t)p] = ((unsigned long long)H.row_off[p] << ROWDEG_SHIFT) | (unsigned long long)d;
+    H.label[(size_t)p] = H.rank_of[order[p]];
   }
-  const int64_t E = row_off[M];
-  s->E = E;
-  std::vector<int> item_pos;
-  std::vector<long long> item_off;
-  std::vector<int> item_len;
+  const int64_t E = H.row_off[M];
+  H.E = E;
   for (int c = 0; c < 2; c++)
-    for (int cls = 1; cls < 3; cls++) {
-      s->item_begin[c][cls - 1] = (int)item_pos.size();
-      for (int p = cls_begin[c][cls]; p < cls_end[c][cls]; p++) {
-        if (owner_of_pos[(size_t)p] != rank) continue;  // multi-GPU: somebody else's node
-        const long long d = row_off[(size_t)p + 1] - row_off[p];
-        if (d > s->max_deg_par) s->max_deg_par = (int32_t)std::min<long long>(d, INT32_MAX);
-        if (cls == 2 && d > s->chunk) s->hub_items[c] += (int)((d + s->chunk - 1) / s->chunk);
-        for (long long o = 0; o < d; o += s->chunk) {
-          item_pos.push_back(p);
-          item_off.push_back(row_off[p] + o);
-          item_len.push_back((int)std::min<long long>(s->chunk, d - o));
-        }
-      }
-      s->item_end[c][cls - 1] = (int)item_pos.size();
-    }
-  s->n_items = (int)item_pos.size();
-  for (int c = 0; c < 2; c++)
-    for (int p = cls_begin[c][0]; p < cls_end[c][0]; p++)
-      s->max_deg_seq = std::max<int32_t>(s->max_deg_seq, (int32_t)std::min<long long>(row_off[(size_t)p + 1] - row_off[p], INT32_MAX));
-  const double t_items = now_ms();
+    for (int p = H.cls_begin[c][0]; p < H.cls_end[c][0]; p++)
+      H.max_deg_seq = std::max<int32_t>(H.max_deg_seq, (int32_t)std::min<long long>(H.row_off[(size_t)p + 1] - H.row_off[p], INT32_MAX));
+  const double t_off = now_ms();
   // column words: one lookup table (word of every node), then a parallel gather over edge-balanced position ranges
-  std::vector<uint32_t> enc((size_t)std::max<int64_t>(E, 1));
+  H.enc.assign((size_t)std::max<int64_t>(E, 1), 0u);
   {
     std::vector<uint32_t> word_of((size_t)n);
     host_parallel_for(n, 1 << 15, [&](int, int64_t lo, int64_t hi) {
       for (int64_t v = lo; v < hi; v++)
-        word_of[(size_t)v] = pos_of[(size_t)v] < 0 ? (COL_SINK | (uint32_t)rank_of[(size_t)v])
-                                                    : ((uint32_t)pos_of[(size_t)v] | ((uint32_t)colour[(size_t)v] << COL_COLOUR_SHIFT));
+        word_of[(size_t)v] = H.pos_of[(size_t)v] < 0 ? (COL_SINK | (uint32_t)H.rank_of[(size_t)v])
+                                                      : ((uint32_t)H.pos_of[(size_t)v] | ((uint32_t)colour[(size_t)v] << COL_COLOUR_SHIFT));
     });
     const int parts = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), E / (1 << 15)));
     host_parallel(parts, [&](int t) {
-      const int32_t p_lo = (int32_t)(std::lower_bound(row_off.begin(), row_off.end(), (long long)(E * t / parts)) - row_off.begin());
-      const int32_t p_hi = t + 1 == parts ? M : (int32_t)(std::lower_bound(row_off.begin(), row_off.end(), (long long)(E * (t + 1) / parts)) - row_off.begin());
+      const int32_t p_lo = (int32_t)(std::lower_bound(H.row_off.begin(), H.row_off.end(), (long long)(E * t / parts)) - H.row_off.begin());
+      const int32_t p_hi = t + 1 == parts ? M : (int32_t)(std::lower_bound(H.row_off.begin(), H.row_off.end(), (long long)(E * (t + 1) / parts)) - H.row_off.begin());
       for (int32_t p = p_lo; p < p_hi; p++) {
         const int32_t v = order[(size_t)p];
-        long long o = row_off[(size_t)p];
-        for (int64_t i = row_ptr[v]; i < row_ptr[v + 1]; i++) enc[(size_t)o++] = word_of[(size_t)col[i]];
+        long long o = H.row_off[(size_t)p];
+        for (int64_t i = row_ptr[v]; i < row_ptr[v + 1]; i++) H.enc[(size_t)o++] = word_of[(size_t)col[i]];
       }
     });
   }
-  s->prep_ms = now_ms() - t0;
+  H.prep_ms = now_ms() - t0;
   if (getenv("PPRB200_HOST_TIMING"))
-    fprintf(stderr, "[pprb200] host prep %.2f ms: colour %.2f, storage order %.2f, rank labels %.2f, offsets+items %.2f, encode %.2f (%d threads)\n",
-            s->prep_ms, t_col - t0, t_ord - t_col, t_rank - t_ord, t_items - t_rank, now_ms() - t_items, host_threads());
-  if (plan_out) {
-    const HostPlanOut& o = *plan_out;
-    if (o.pos_of) std::memcpy(o.pos_of, pos_of.data(), sizeof(int32_t) * (size_t)n);
-    if (o.rank_of) std::memcpy(o.rank_of, rank_of.data(), sizeof(int32_t) * (size_t)n);
-    if (o.row_off) for (int32_t p = 0; p <= M; p++) o.row_off[p] = row_off[(size_t)p];
-    if (o.enc && E) std::memcpy(o.enc, enc.data(), sizeof(uint32_t) * (size_t)E);
-    const int32_t ni = std::min<int32_t>(s->n_items, o.item_cap);
-    for (int32_t i = 0; i < ni; i++) {
-      if (o.item_pos) o.item_pos[i] = item_pos[(size_t)i];
-      if (o.item_off) o.item_off[i] = item_off[(size_t)i];
-      if (o.item_len) o.item_len[i] = item_len[(size_t)i];
-    }
-    if (o.summary) {
-      int32_t* q = o.summary;
-      q[0] = M; q[1] = s->n_items; q[2] = s->chunk; q[3] = s->mid_deg;
-      for (int c = 0; c < 2; c++) { q[4 + c] = s->range_begin[c]; q[6 + c] = s->range_end[c]; }
-      for (int c = 0; c < 2; c++)
-        for (int k = 0; k < 2; k++) { q[8 + 2 * c + k] = s->item_begin[c][k]; q[12 + 2 * c + k] = s->item_end[c][k]; }
-    }
-    delete s;
-    return PPRB200_OK;
-  }
+    fprintf(stderr, "[pprb200] host plan %.2f ms: colour %.2f, storage order %.2f, rank labels %.2f, offsets %.2f, encode %.2f (%d threads)\n",
+            H.prep_ms, t_col - t0, t_ord - t_col, t_rank - t_ord, t_off - t_rank, now_ms() - t_off, host_threads());
+  return PPRB200_OK;
+}
 
+static void build_rank_plan(const HostPlan& H, int32_t rank, RankPlan& R) {
+  const int world = H.world;
+  for (int c = 0; c < 2; c++) {
+    if (world == 1) {
+      R.range_begin[c] = H.cls_begin[c][0];
+      R.range_end[c] = H.cls_end[c][0];
+    } else {
+      R.range_begin[c] = (int)R.seq_list.size();
+      for (int p = H.cls_begin[c][0]; p < H.cls_end[c][0]; p++)
+        if (H.owner_of_pos[(size_t)p] == rank) R.seq_list.push_back(p);
+      R.range_end[c] = (int)R.seq_list.size();
+    }
+  }
+  for (int c = 0; c < 2; c++)
+    for (int cls = 1; cls < 3; cls++) {
+      R.item_begin[c][cls - 1] = (int)R.item_pos.size();
+      for (int p = H.cls_begin[c][cls]; p < H.cls_end[c][cls]; p++) {
+        if (H.owner_of_pos[(size_t)p] != rank) continue;  // multi-GPU: somebody else's node
+        const long long d = H.row_off[(size_t)p + 1] - H.row_off[p];
+        if (d > R.max_deg_par) R.max_deg_par = (int32_t)std::min<long long>(d, INT32_MAX);
+        if (cls == 2 && d > H.chunk) R.hub_items[c] += (int)((d + H.chunk - 1) / H.chunk);
+        for (long long o = 0; o < d; o += H.chunk) {
+          R.item_pos.push_back(p);
+          R.item_off.push_back(H.row_off[p] + o);
+          R.item_len.push_back((int)std::min<long long>(H.chunk, d - o));
+        }
+      }
+      R.item_end[c][cls - 1] = (int)R.item_pos.size();
+    }
+}
+
+// allocate + upload one rank's session on the CURRENT device
+static int session_from_plan(const HostPlan& H, const RankPlan& R, uint32_t max_L, int32_t rank, void* stream, bool ipc,
+                             pprb200_session** out) {
+  int rc;
+  *out = nullptr;
   const double t1 = now_ms();
+  pprb200_session* s = new pprb200_session();
+  std::memset(&s->peers, 0, sizeof(s->peers));
+  std::memset(s->ipc_opened, 0, sizeof(s->ipc_opened));
+  pool_setup_once();
+  g_alloc_stream = (cudaStream_t)stream;
+  const int32_t n = H.n, M = H.M;
+  const int64_t E = H.E;
+  const int world = H.world;
+  s->n = n; s->M = M; s->E = E;
+  s->max_L = max_L;
+  s->hub_threshold = H.hub_threshold;
+  s->rank = rank;
+  s->world = world;
+  s->ipc = ipc;
+  s->stream = (cudaStream_t)stream;
+  cudaGetDevice(&s->device);
+  cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
+  s->chunk = H.chunk; s->mid_deg = H.mid_deg;
+  s->max_deg = H.max_deg; s->max_deg_seq = H.max_deg_seq; s->max_deg_par = R.max_deg_par;
+  for (int c = 0; c < 2; c++) {
+    s->colour_count[c] = H.colour_count[c];
+    s->range_begin[c] = R.range_begin[c]; s->range_end[c] = R.range_end[c];
+    s->hub_items[c] = R.hub_items[c];
+    for (int k = 0; k < 2; k++) { s->item_begin[c][k] = R.item_begin[c][k]; s->item_end[c][k] = R.item_end[c][k]; }
+  }
+  s->n_items = (int)R.item_pos.size();
+  s->prep_ms = H.prep_ms;
   // a basket never holds more than n keys: slots are sized for min(max_L, n) (runs clamp L the same way), so that the
   // reference's grank(graph, graph.size(), 2 * graph.size(), ...) pattern (test/grankTest.cc:261-283) costs nothing extra
   const int Lp = roundup4((int)effective_L(max_L, n));
   s->buf_bytes = (size_t)std::max(M, 1) * slot_bytes(Lp);
-  if ((rc = dev_alloc(&s->d_row_off, (size_t)M + 1)) || (rc = dev_alloc(&s->d_col, (size_t)E)) ||
+  if ((rc = dev_alloc(&s->d_row_off, (size_t)M + 1)) || (rc = dev_alloc(&s->d_col, (size_t)E)) || (rc = dev_alloc(&s->d_rowdeg, (size_t)std::max(M, 1))) ||
       (rc = dev_alloc(&s->d_label, (size_t)M)) || (rc = dev_alloc(&s->d_pos_of, (size_t)n)) || (rc = dev_alloc(&s->d_dense_of, (size_t)n)) ||
-      (rc = dev_alloc(&s->d_colour, (size_t)n)) || (rc = dev_alloc(&s->d_buf[0], s->buf_bytes, world > 1)) ||
-      (rc = dev_alloc(&s->d_buf[1], s->buf_bytes, world > 1)) || (rc = dev_alloc(&s->d_queue[0], (size_t)M)) ||
+      (rc = dev_alloc(&s->d_colour, (size_t)n)) || (rc = dev_alloc(&s->d_buf[0], s->buf_bytes, ipc)) ||
+      (rc = dev_alloc(&s->d_buf[1], s->buf_bytes, ipc)) || (rc = dev_alloc(&s->d_queue[0], (size_t)M)) ||
       (rc = dev_alloc(&s->d_queue[1], (size_t)M)) || (rc = dev_alloc(&s->d_queue[2], (size_t)M)) || (rc = dev_alloc(&s->d_queue[3], (size_t)M)) ||
       (rc = dev_alloc(&s->d_ncand, (size_t)M)) || (rc = dev_alloc(&s->d_state, 1)) ||
       (rc = dev_alloc(&s->d_final_stats, 2))) {
@@ -603,17 +644,16 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
     cudaError_t _e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);                   \
     if (_e != cudaSuccess) { session_free(s); return fail(PPRB200_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(_e)); } \
   } while (0)
-  UP(s->d_row_off, row_off.data(), ((size_t)M + 1) * sizeof(long long));
-  if (E) UP(s->d_col, enc.data(), (size_t)E * sizeof(uint32_t));
-  std::vector<int32_t> label((size_t)std::max(M, 1));
-  for (int32_t p = 0; p < M; p++) label[p] = rank_of[order[p]];
-  if (M) UP(s->d_label, label.data(), (size_t)M * sizeof(int));
-  if (n) UP(s->d_dense_of, dense_of.data(), (size_t)n * sizeof(int));
-  if (n) UP(s->d_pos_of, pos_of.data(), (size_t)n * sizeof(int));
-  if (n) UP(s->d_colour, colour.data(), (size_t)n);
+  UP(s->d_row_off, H.row_off.data(), ((size_t)M + 1) * sizeof(long long));
+  if (M) UP(s->d_rowdeg, H.rowdeg.data(), (size_t)M * sizeof(unsigned long long));
+  if (E) UP(s->d_col, H.enc.data(), (size_t)E * sizeof(uint32_t));
+  if (M) UP(s->d_label, H.label.data(), (size_t)M * sizeof(int));
+  if (n) UP(s->d_dense_of, H.dense_of.data(), (size_t)n * sizeof(int));
+  if (n) UP(s->d_pos_of, H.pos_of.data(), (size_t)n * sizeof(int));
+  if (n) UP(s->d_colour, H.colour.data(), (size_t)n);
   if (world > 1) {
-    if ((rc = dev_alloc(&s->d_seq_list, seq_list.size()))) { session_free(s); return rc; }
-    if (!seq_list.empty()) UP(s->d_seq_list, seq_list.data(), seq_list.size() * sizeof(int));
+    if ((rc = dev_alloc(&s->d_seq_list, R.seq_list.size()))) { session_free(s); return rc; }
+    if (!R.seq_list.empty()) UP(s->d_seq_list, R.seq_list.data(), R.seq_list.size() * sizeof(int));
   }
   if (s->n_items > 0) {
     // global-table pool of the order-free path: one table per CTA that can be in flight, sized for the worst case of
@@ -644,9 +684,9 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
       session_free(s);
       return rc;
     }
-    UP(s->d_item_pos, item_pos.data(), (size_t)s->n_items * sizeof(int));
-    UP(s->d_item_off, item_off.data(), (size_t)s->n_items * sizeof(long long));
-    UP(s->d_item_len, item_len.data(), (size_t)s->n_items * sizeof(int));
+    UP(s->d_item_pos, R.item_pos.data(), (size_t)s->n_items * sizeof(int));
+    UP(s->d_item_off, R.item_off.data(), (size_t)s->n_items * sizeof(long long));
+    UP(s->d_item_len, R.item_len.data(), (size_t)s->n_items * sizeof(int));
     cudaMemsetAsync(s->d_tbl_inuse, 0, (size_t)n_tables * sizeof(unsigned int), st);
     cudaMemsetAsync(s->d_tbl_count, 0, (size_t)n_tables * sizeof(unsigned int), st);
     cudaMemsetAsync(s->d_node_tbl, 0, (size_t)M * sizeof(unsigned int), st);
@@ -656,10 +696,10 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
                                                         s->tbl_count_cls[cls]);
   }
 #undef UP
-  cudaError_t e = cudaStreamSynchronize(st);  // host vectors go out of scope
+  cudaError_t e = cudaStreamSynchronize(st);  // (the plan's vectors may go out of scope)
   if (e != cudaSuccess) { session_free(s); return fail(PPRB200_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e)); }
   cudaMemsetAsync(s->d_ncand, 0, (size_t)std::max(M, 1) * sizeof(int), st);
-  if ((rc = dev_alloc(&s->d_mbox, (size_t)2 * MAX_WORLD, world > 1))) { session_free(s); return rc; }
+  if ((rc = dev_alloc(&s->d_mbox, (size_t)2 * MAX_WORLD, ipc))) { session_free(s); return rc; }
   cudaMemsetAsync(s->d_mbox, 0, sizeof(Mailbox) * 2 * MAX_WORLD, st);
   cudaMemsetAsync(s->d_state, 0, sizeof(RunState), st);
   cudaEventCreate(&s->ev_begin);
@@ -672,17 +712,57 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   }
   cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
   s->cur = s->stream;
-  if (const char* e = getenv("PPRB200_OVERLAP")) s->overlap = atoi(e) != 0;
+  if (const char* ev = getenv("PPRB200_OVERLAP")) s->overlap = atoi(ev) != 0;
   s->use_dense = dense_enabled();
-  if (const char* e = getenv("PPRB200_DENSE_THREADS")) s->dense_threads = atoi(e) == 512 ? 512 : 1024;
+  if (const char* ev = getenv("PPRB200_DENSE_THREADS")) s->dense_threads = atoi(ev) == 512 ? 512 : 1024;
   if (getenv("PPRB200_PROF")) {
     if ((rc = dev_alloc(&s->d_prof, (size_t)2 * s->sm_count * 8 * 8))) { session_free(s); return rc; }
     cudaMemsetAsync(s->d_prof, 0, (size_t)2 * s->sm_count * 8 * 8 * sizeof(unsigned long long), st);
   }
   s->h2d_ms = now_ms() - t1;
-  if (getenv("PPRB200_HOST_TIMING")) fprintf(stderr, "[pprb200] device setup + H2D %.2f ms\n", s->h2d_ms);
+  if (getenv("PPRB200_HOST_TIMING")) fprintf(stderr, "[pprb200] rank %d: device setup + H2D %.2f ms\n", rank, s->h2d_ms);
   *out = s;
   return PPRB200_OK;
+}
+
+static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour_in,
+                               uint32_t max_L, uint32_t hub_threshold, int32_t rank, int32_t world, void* stream,
+                               pprb200_session** out, bool need_colour = true, const HostPlanOut* plan_out = nullptr) {
+  if (!out) return fail(PPRB200_ERR_PARAM, "out is NULL");
+  *out = nullptr;
+  if (max_L == 0) return fail(PPRB200_ERR_PARAM, "L must be positive");
+  if (world < 1 || world > MAX_WORLD || rank < 0 || rank >= world) return fail(PPRB200_ERR_PARAM, "rank %d / world %d: need 0 <= rank < world <= %d", rank, world, MAX_WORLD);
+  int rc = validate_csr(row_ptr, col, n);
+  if (rc) return rc;
+  if (!plan_out && (rc = device_ok())) return rc;
+  HostPlan H;
+  if ((rc = build_host_plan(row_ptr, col, n, colour_in, hub_threshold, world, need_colour, H))) return rc;
+  RankPlan R;
+  build_rank_plan(H, rank, R);
+  if (plan_out) {
+    const HostPlanOut& o = *plan_out;
+    const int32_t M = H.M;
+    if (o.pos_of) std::memcpy(o.pos_of, H.pos_of.data(), sizeof(int32_t) * (size_t)n);
+    if (o.rank_of) std::memcpy(o.rank_of, H.rank_of.data(), sizeof(int32_t) * (size_t)n);
+    if (o.row_off) for (int32_t p = 0; p <= M; p++) o.row_off[p] = H.row_off[(size_t)p];
+    if (o.enc && H.E) std::memcpy(o.enc, H.enc.data(), sizeof(uint32_t) * (size_t)H.E);
+    const int32_t n_items = (int32_t)R.item_pos.size();
+    const int32_t ni = std::min<int32_t>(n_items, o.item_cap);
+    for (int32_t i = 0; i < ni; i++) {
+      if (o.item_pos) o.item_pos[i] = R.item_pos[(size_t)i];
+      if (o.item_off) o.item_off[i] = R.item_off[(size_t)i];
+      if (o.item_len) o.item_len[i] = R.item_len[(size_t)i];
+    }
+    if (o.summary) {
+      int32_t* q = o.summary;
+      q[0] = M; q[1] = n_items; q[2] = H.chunk; q[3] = H.mid_deg;
+      for (int c = 0; c < 2; c++) { q[4 + c] = R.range_begin[c]; q[6 + c] = R.range_end[c]; }
+      for (int c = 0; c < 2; c++)
+        for (int k = 0; k < 2; k++) { q[8 + 2 * c + k] = R.item_begin[c][k]; q[12 + 2 * c + k] = R.item_end[c][k]; }
+    }
+    return PPRB200_OK;
+  }
+  return session_from_plan(H, R, max_L, rank, stream, /*ipc=*/world > 1, out);
 }
 
 // ---- stage configuration -----------------------------------------------------------------------
@@ -700,11 +780,11 @@ static unsigned int next_pow2(unsigned long long x) {
 template <int CAP, int WARPS, typename IdxT>
 static cudaError_t launch_stage(pprb200_session* s, const MergeParams& P, int grid, size_t smem, unsigned char* ws,
                                 unsigned int ws_cap, int ws_identity) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};  // cudaFuncSetAttribute is per device
+  if (!configured[s->device & 63]) {
     cudaError_t e = cudaFuncSetAttribute(merge_seq_kernel<CAP, WARPS, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[s->device & 63] = true;
   }
   merge_seq_kernel<CAP, WARPS, IdxT><<<grid, WARPS * 32, smem, s->cur>>>(P, ws, ws_cap, ws_identity);
   s->launch_count++;
@@ -782,11 +862,11 @@ static int enqueue_cascade(pprb200_session* s, MergeParams P, int range_begin, i
 template <int H, int TCAP, int CMAX, int COLCAP, int R, int THREADS>
 static cudaError_t launch_par(pprb200_session* s, const ParParams& P, int grid) {
   const size_t smem = par_smem_bytes<H, TCAP, CMAX, COLCAP, R>() + 8 + par_queue_bytes(THREADS);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};
+  if (!configured[s->device & 63]) {
     cudaError_t e = cudaFuncSetAttribute(merge_par_kernel<H, TCAP, CMAX, COLCAP, R, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[s->device & 63] = true;
   }
   merge_par_kernel<H, TCAP, CMAX, COLCAP, R, THREADS><<<grid, THREADS, smem, s->cur>>>(P);
   s->launch_count++;
@@ -797,12 +877,10 @@ template <int H, int R, int TCAP, int CMAX, int COLCAP, int THREADS, int MINB>
 static cudaError_t launch_dense(pprb200_session* s, const DenseParams& P, int grid) {
   const size_t smem = dense_smem_bytes<H, R, TCAP, CMAX, COLCAP>();
   static bool configured[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!configured[dev & 63]) {
+  if (!configured[s->device & 63]) {
     cudaError_t e = cudaFuncSetAttribute(merge_dense_kernel<H, R, TCAP, CMAX, COLCAP, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured[dev & 63] = true;
+    configured[s->device & 63] = true;
   }
   merge_dense_kernel<H, R, TCAP, CMAX, COLCAP, THREADS, MINB><<<grid, THREADS, smem, s->cur>>>(P);
   s->launch_count++;
@@ -875,8 +953,13 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
       if (cls == 1)
         err = s->dense_threads == 512 ? launch_dense<8192, 16384, 2048, 2048, 1024, 512, 1>(s, D, std::min(s->sm_count, D.n_items))
                                       : launch_dense<8192, 16384, 2048, 2048, 1024, 1024, 1>(s, D, std::min(s->sm_count, D.n_items));
-      else
-        err = launch_dense<4096, 8192, 2048, 1024, PAR_MID_MAX, 512, 2>(s, D, std::min(s->sm_count * 2, D.n_items));
+      else {
+        static const int cfg = getenv("PPRB200_MID_CFG") ? atoi(getenv("PPRB200_MID_CFG")) : 0;  // A/B hook
+        if (cfg == 1) err = launch_dense<2048, 4096, 512, 512, PAR_MID_MAX, 128, 4>(s, D, std::min(s->sm_count * 4, D.n_items));
+        else if (cfg == 2) err = launch_dense<1024, 8192, 512, 512, PAR_MID_MAX, 128, 4>(s, D, std::min(s->sm_count * 4, D.n_items));
+        else if (cfg == 3) err = launch_dense<2048, 8192, 1024, 512, PAR_MID_MAX, 256, 3>(s, D, std::min(s->sm_count * 3, D.n_items));
+        else err = launch_dense<4096, 8192, 2048, 1024, PAR_MID_MAX, 512, 2>(s, D, std::min(s->sm_count * 2, D.n_items));
+      }
       if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_dense launch failed: %s", cudaGetErrorString(err));
     }
   }
@@ -942,11 +1025,11 @@ static int enqueue_final(pprb200_session* s, int L, uint32_t K, double sink_scor
   const int Lp = roundup4(L);
   const int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(200 * 1024) / ((size_t)Lp * 12)));
   const size_t smem = (size_t)warps * Lp * 12;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static size_t configured[64] = {0};
+  if (smem > 48 * 1024 && smem > configured[s->device & 63]) {
     cudaError_t e = cudaFuncSetAttribute(final_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "final_topk smem %zu: %s", smem, cudaGetErrorString(e));
-    configured = smem;
+    configured[s->device & 63] = smem;
   }
   cudaMemsetAsync(s->d_final_stats, 0, 2 * sizeof(unsigned long long), s->stream);
   const int grid = std::max(1, std::min((s->n + warps - 1) / warps, s->sm_count * 8));
@@ -1038,12 +1121,12 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
 // ---- MCCompletePathV2 (mccompletepathv2.h:182-258, north-star semantics) ---------------------------------------
 template <bool GLOBAL, int THREADS>
 static cudaError_t launch_walk_t(pprb200_session* s, const WalkParams& P, int grid, size_t smem) {
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static size_t configured[64] = {0};
+  if (smem > 48 * 1024 && smem > configured[s->device & 63]) {
     cudaError_t e = cudaFuncSetAttribute(mc_walk_kernel<GLOBAL, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaFuncSetAttribute(mc_walk_kernel<GLOBAL, THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = smem;
+    configured[s->device & 63] = smem;
   }
   mc_walk_kernel<GLOBAL, THREADS><<<grid, THREADS, smem, s->stream>>>(P);
   s->launch_count++;
@@ -1098,6 +1181,7 @@ static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t 
     P.M = s->M; P.src_begin = 0; P.src_end = s->M; P.n_ids = s->n;
     P.colour = s->d_colour;
     P.peers = s->peers;
+    P.rowdeg = s->d_rowdeg;
     P.Lp = Lp; P.L = (int)L; P.R = R; P.W = W; P.thresh = mc_coin_threshold(damping); P.seed = seed;
     // shared-memory table sized for the expected number of distinct visited nodes (<= hops + 1)
     const double len = damping >= 1.0 ? (double)MC_MAX_STEPS : std::min<double>((double)MC_MAX_STEPS, 1.0 / (1.0 - damping));
@@ -1185,7 +1269,7 @@ static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t 
   return PPRB200_OK;
 }
 
-static int session_stats_impl(pprb200_session* s, pprb200_stats* out) {
+static int session_stats_impl(pprb200_session* s, pprb200_stats* out, bool with_final = true) {
   if (!out) return fail(PPRB200_ERR_PARAM, "stats is NULL");
   std::memset(out, 0, sizeof(*out));
   if (s->last_mode < 0) return fail(PPRB200_ERR_STATE, "no run has been enqueued on this session");
@@ -1207,8 +1291,8 @@ static int session_stats_impl(pprb200_session* s, pprb200_stats* out) {
   out->edge_reads = h.edge_reads;
   out->merged_entries = h.merged;
   out->candidates = h.cands;
-  out->truncations = h.truncs + fin[0];
-  out->boundary_ties = h.ties + fin[1];
+  out->truncations = h.truncs + (with_final ? fin[0] : 0);  // (every rank runs the final top-K over all nodes: counted once)
+  out->boundary_ties = h.ties + (with_final ? fin[1] : 0);
   out->algorithmic_bytes = h.abytes;
   out->walk_steps = h.walk_steps;
   out->walks = h.walks;
@@ -1338,6 +1422,33 @@ static long long peer_timeout_cycles() {
   double ms = 30000.0;
   if (const char* e = getenv("PPRB200_PEER_TIMEOUT_MS")) ms = std::max(1.0, atof(e));
   return (long long)(ms * 2.0e6);
+}
+
+// debug: out[i][4] = Philox4x32-10(counter = ctr_key[i][0..3], key = ctr_key[i][4..5]) computed by the device function of mc_walk.cuh
+int pprb200_debug_philox(const uint32_t* ctr_key, uint32_t* out, int32_t nblocks) {
+  if (!ctr_key || !out || nblocks <= 0) return fail(PPRB200_ERR_PARAM, "bad argument");
+  int rc = device_ok();
+  if (rc) return rc;
+  uint32_t *d_in = nullptr, *d_out = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&d_in, (size_t)nblocks * 24));
+  CUDA_TRY(cudaMalloc((void**)&d_out, (size_t)nblocks * 16));
+  CUDA_TRY(cudaMemcpy(d_in, ctr_key, (size_t)nblocks * 24, cudaMemcpyHostToDevice));
+  philox_probe_kernel<<<(nblocks + 127) / 128, 128>>>(d_in, d_out, nblocks);
+  cudaError_t e = cudaMemcpy(out, d_out, (size_t)nblocks * 16, cudaMemcpyDeviceToHost);
+  cudaFree(d_in);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "philox probe failed: %s", cudaGetErrorString(e));
+  return PPRB200_OK;
+}
+
+// debug: merge_dense_kernel bookkeeping of the last run (RunState::dbg), out[8]
+int pprb200_debug_counters(pprb200_session* s, unsigned long long* out) {
+  if (!s || !out) return fail(PPRB200_ERR_PARAM, "NULL argument");
+  cudaStreamSynchronize(s->stream);
+  RunState h;
+  CUDA_TRY(cudaMemcpy(&h, s->d_state, sizeof(h), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 8; i++) out[i] = h.dbg[i];
+  return PPRB200_OK;
 }
 
 // ---- multi-GPU wiring: CUDA IPC handles of the two basket buffers and the mailbox ----------------------------------
@@ -1549,6 +1660,141 @@ int pprb200_session_launches(pprb200_session* s, uint64_t* launches) {
   return PPRB200_OK;
 }
 
+// ---- the one-shot entry points (what the template headers call) --------------------------------------------------
+// GPUs of a one-shot call: PPR_NUM_GPUS from the environment, else every usable device as far as the graph
+// gives each of them work (one GPU per 8 M edges: below that the per-iteration exchange and the 8 uploads cost more than they
+// save), at most MAX_WORLD. Multi-GPU runs live in ONE process: a session per device sharing one host plan, peer access
+// between the devices (cudaDeviceEnablePeerAccess; no IPC), the same kernels and mailbox barriers as the process-per-GPU path.
+static int oneshot_world(int64_t n_edges) {
+  const int avail = std::min(pprb200_device_count(), (int)MAX_WORLD);
+  if (avail <= 1) return 1;
+  if (const char* e = getenv("PPR_NUM_GPUS")) return std::max(1, std::min(avail, atoi(e)));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(avail, n_edges / (8ll << 20)));
+}
+
+struct OneShot {
+  int mode;  // MODE_GRANK / MODE_MC
+  uint32_t K, L, iterations;  // iterations = R for MC
+  double damping, tolerance;
+  uint64_t seed;
+  uint32_t rounds;
+};
+
+static int run_oneshot(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour, uint32_t hub_threshold,
+                       const OneShot& job, int32_t* out_ids, double* out_scores, uint32_t* out_cnt, pprb200_stats* stats) {
+  const double t0 = now_ms();
+  int rc = validate_csr(row_ptr, col, n);
+  if (rc) return rc;
+  if ((rc = device_ok())) return rc;
+  const int world = oneshot_world(row_ptr[n]);
+  int dev0 = 0;
+  cudaGetDevice(&dev0);
+  std::vector<int> devs;  // sm_100 devices, the current one first
+  {
+    int cnt = 0;
+    cudaGetDeviceCount(&cnt);
+    devs.push_back(dev0);
+    for (int d = 0; d < cnt && (int)devs.size() < world; d++) {
+      int major = 0;
+      if (d != dev0 && cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) devs.push_back(d);
+    }
+  }
+  std::vector<pprb200_session*> ss((size_t)world, nullptr);
+  std::vector<cudaStream_t> streams((size_t)world, nullptr);
+  auto cleanup = [&]() {
+    for (int r = 0; r < world; r++) {
+      cudaSetDevice(devs[(size_t)r]);
+      if (ss[(size_t)r]) { cudaStreamSynchronize(ss[(size_t)r]->stream); session_free(ss[(size_t)r]); }
+      if (streams[(size_t)r]) cudaStreamDestroy(streams[(size_t)r]);
+    }
+    cudaSetDevice(dev0);
+  };
+  double t_plan = 0, t_up = 0, t_enq = 0, t_run = 0, t_d2h = 0;
+  {
+    HostPlan H;
+    if ((rc = build_host_plan(row_ptr, col, n, colour, hub_threshold, world, job.mode == MODE_GRANK, H))) return rc;
+    t_plan = now_ms();
+    if (world > 1) {
+      for (int a = 0; a < world && !rc; a++) {
+        cudaSetDevice(devs[(size_t)a]);
+        for (int b2 = 0; b2 < world; b2++) {
+          if (a == b2) continue;
+          int can = 0;
+          cudaDeviceCanAccessPeer(&can, devs[(size_t)a], devs[(size_t)b2]);
+          if (!can) { rc = fail(PPRB200_ERR_CUDA, "device %d cannot access device %d: set PPR_NUM_GPUS=1", devs[(size_t)a], devs[(size_t)b2]); break; }
+          const cudaError_t e = cudaDeviceEnablePeerAccess(devs[(size_t)b2], 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { rc = fail(PPRB200_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", devs[(size_t)a], devs[(size_t)b2], cudaGetErrorString(e)); break; }
+          cudaGetLastError();
+        }
+      }
+      if (rc) { cudaSetDevice(dev0); return rc; }
+    }
+    for (int r = 0; r < world; r++) {
+      cudaSetDevice(devs[(size_t)r]);
+      if (world > 1) cudaStreamCreateWithFlags(&streams[(size_t)r], cudaStreamNonBlocking);
+      RankPlan R;
+      build_rank_plan(H, r, R);
+      if ((rc = session_from_plan(H, R, job.L, r, streams[(size_t)r], /*plain cudaMalloc for peer-visible buffers*/ world > 1, &ss[(size_t)r]))) { cleanup(); return rc; }
+    }
+    t_up = now_ms();
+  }
+  if (world > 1) {
+    for (int r = 0; r < world; r++) {
+      PeerDev pd;
+      std::memset(&pd, 0, sizeof(pd));
+      pd.world = world;
+      pd.rank = r;
+      pd.timeout_cycles = peer_timeout_cycles();
+      for (int q = 0; q < world; q++) { pd.buf[q][0] = ss[(size_t)q]->d_buf[0]; pd.buf[q][1] = ss[(size_t)q]->d_buf[1]; pd.mbox[q] = ss[(size_t)q]->d_mbox; }
+      ss[(size_t)r]->peers = pd;
+      ss[(size_t)r]->attached = true;
+    }
+    for (int r = 0; r < world; r++) { cudaSetDevice(devs[(size_t)r]); cudaStreamSynchronize(ss[(size_t)r]->stream); }  // mailboxes zeroed everywhere before anybody posts
+  }
+  for (int r = 0; r < world && !rc; r++) {
+    cudaSetDevice(devs[(size_t)r]);
+    rc = job.mode == MODE_GRANK ? session_grank_impl(ss[(size_t)r], job.K, job.L, job.iterations, job.damping, job.tolerance)
+                                : session_mc_impl(ss[(size_t)r], job.K, job.L, job.iterations, job.damping, job.seed, job.rounds);
+  }
+  t_enq = now_ms();
+  if (!rc) {
+    for (int r = 0; r < world; r++) { cudaSetDevice(devs[(size_t)r]); cudaStreamSynchronize(ss[(size_t)r]->stream); }
+    t_run = now_ms();
+    cudaSetDevice(devs[0]);
+    rc = session_fetch_impl(ss[0], out_ids, out_scores, out_cnt);  // every rank holds every basket: rank 0's final top-K is the result
+    t_d2h = now_ms() - t_run;
+  }
+  if (!rc && stats) {
+    pprb200_stats acc;
+    std::memset(&acc, 0, sizeof(acc));
+    for (int r = 0; r < world && !rc; r++) {
+      cudaSetDevice(devs[(size_t)r]);
+      pprb200_stats st;
+      rc = session_stats_impl(ss[(size_t)r], &st, /*with_final=*/r == 0);
+      if (rc) break;
+      if (r == 0) acc = st;
+      else {
+        acc.nonsink_node_iterations += st.nonsink_node_iterations; acc.edge_reads += st.edge_reads; acc.merged_entries += st.merged_entries;
+        acc.candidates += st.candidates; acc.truncations += st.truncations; acc.boundary_ties += st.boundary_ties;
+        acc.algorithmic_bytes += st.algorithmic_bytes; acc.walk_steps += st.walk_steps; acc.walks += st.walks;
+        acc.overflow_requeues += st.overflow_requeues; acc.walk_algorithmic_bytes += st.walk_algorithmic_bytes;
+        acc.kernel_ms = std::max(acc.kernel_ms, st.kernel_ms);
+        acc.h2d_ms += st.h2d_ms;
+      }
+    }
+    acc.n_gpus = (uint32_t)world;
+    acc.d2h_ms = t_d2h;
+    *stats = acc;
+  }
+  const double t_f0 = now_ms();
+  cleanup();
+  if (getenv("PPRB200_HOST_TIMING"))
+    fprintf(stderr, "[pprb200] one-shot call on %d GPU(s): plan %.2f ms, upload %.2f, enqueue %.2f, wait %.2f, fetch %.2f, free %.2f\n", world,
+            t_plan - t0, t_up - t_plan, t_enq - t_up, t_run - t_enq, t_d2h, now_ms() - t_f0);
+  if (!rc && stats) stats->total_ms = now_ms() - t0;
+  return rc;
+}
+
 int pprb200_grank(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour, uint32_t K, uint32_t L,
                   uint32_t iterations, double damping, double tolerance, uint32_t hub_threshold, int32_t* out_ids,
                   double* out_scores, uint32_t* out_cnt, pprb200_stats* stats) {
@@ -1556,35 +1802,11 @@ int pprb200_grank(const int64_t* row_ptr, const int32_t* col, int32_t n, const u
   if (rc) return rc;
   if (stats) std::memset(stats, 0, sizeof(*stats));
   if (n == 0) return PPRB200_OK;  // empty graph -> empty result (test/grankTest.cc:31-36)
-  const double t0 = now_ms();
-  pprb200_session* s = nullptr;
-  {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
-    rc = session_create_impl(row_ptr, col, n, colour, L, hub_threshold, 0, 1, nullptr, &s);
-    if (rc) return rc;
-    const double t_created = now_ms();
-    rc = session_grank_impl(s, K, L, iterations, damping, tolerance);
-    double t_d2h = 0;
-    const double t_enq = now_ms();
-    double t_run = t_enq;
-    if (!rc) {
-      cudaStreamSynchronize(s->stream);
-      const double t1 = t_run = now_ms();
-      rc = session_fetch_impl(s, out_ids, out_scores, out_cnt);
-      t_d2h = now_ms() - t1;
-    }
-    if (!rc && stats) {
-      rc = session_stats_impl(s, stats);
-      stats->d2h_ms = t_d2h;
-    }
-    const double t_f0 = now_ms();
-    session_free(s);
-    if (getenv("PPRB200_HOST_TIMING"))
-      fprintf(stderr, "[pprb200] grank call: create %.2f ms, enqueue %.2f, wait %.2f, fetch %.2f, stats %.2f, free %.2f\n", t_created - t0,
-              t_enq - t_created, t_run - t_enq, t_d2h, t_f0 - t_run - t_d2h, now_ms() - t_f0);
-  }
-  if (!rc && stats) stats->total_ms = now_ms() - t0;
-  return rc;
+  OneShot job;
+  job.mode = MODE_GRANK; job.K = K; job.L = L; job.iterations = iterations; job.damping = damping; job.tolerance = tolerance;
+  job.seed = 0; job.rounds = 0;
+  std::lock_guard<std::mutex> lk(g_api_mutex);
+  return run_oneshot(row_ptr, col, n, colour, hub_threshold, job, out_ids, out_scores, out_cnt, stats);
 }
 
 int pprb200_mccompletepathv2(const int64_t* row_ptr, const int32_t* col, int32_t n, uint32_t K, uint32_t L, uint32_t R,
@@ -1594,28 +1816,11 @@ int pprb200_mccompletepathv2(const int64_t* row_ptr, const int32_t* col, int32_t
   if (rc) return rc;
   if (stats) std::memset(stats, 0, sizeof(*stats));
   if (n == 0) return PPRB200_OK;
-  const double t0 = now_ms();
-  pprb200_session* s = nullptr;
-  {
-    std::lock_guard<std::mutex> lk(g_api_mutex);
-    rc = session_create_impl(row_ptr, col, n, nullptr, L, hub_threshold, 0, 1, nullptr, &s, /*need_colour=*/false);
-    if (rc) return rc;
-    rc = session_mc_impl(s, K, L, R, damping, seed, rounds);
-    double t_d2h = 0;
-    if (!rc) {
-      cudaStreamSynchronize(s->stream);
-      const double t1 = now_ms();
-      rc = session_fetch_impl(s, out_ids, out_scores, out_cnt);
-      t_d2h = now_ms() - t1;
-    }
-    if (!rc && stats) {
-      rc = session_stats_impl(s, stats);
-      stats->d2h_ms = t_d2h;
-    }
-    session_free(s);
-  }
-  if (!rc && stats) stats->total_ms = now_ms() - t0;
-  return rc;
+  OneShot job;
+  job.mode = MODE_MC; job.K = K; job.L = L; job.iterations = R; job.damping = damping; job.tolerance = 0.0;
+  job.seed = seed; job.rounds = rounds;
+  std::lock_guard<std::mutex> lk(g_api_mutex);
+  return run_oneshot(row_ptr, col, n, nullptr, hub_threshold, job, out_ids, out_scores, out_cnt, stats);
 }
 
 }  // extern "C"

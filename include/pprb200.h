@@ -150,6 +150,16 @@ int pprb200_debug_host_plan(const int64_t* row_ptr, const int32_t* col, int32_t 
                             int32_t rank, int32_t world, int32_t* pos_of, int32_t* rank_of, int64_t* row_off, uint32_t* enc,
                             int32_t* item_pos, int64_t* item_off, int32_t* item_len, int32_t item_cap, int32_t* summary);
 
+/* Debug: per-CTA phase cycle counters of the order-free merge kernels (sessions created with PPRB200_PROF=1 in the
+ * environment; out[2][8 * sm_count][8], cleared by the call) and merge_dense_kernel's bookkeeping of the last run
+ * (out[8]: nodes finished, nodes that ran pass 2, nodes without a lower bound of the cut, hand-overs to merge_par_kernel
+ * by reason -- untrusted contribution, too many candidates, tail table full --, split-hub items passed on). */
+int pprb200_debug_prof(pprb200_session* s, unsigned long long* out, int* n_ctas);
+int pprb200_debug_counters(pprb200_session* s, unsigned long long* out);
+/* Debug / known-answer tests: out[i][0..3] = Philox4x32-10 with counter ctr_key[i][0..3] and key ctr_key[i][4..5], computed on the
+ * device by the generator the walk kernel uses (csrc/mc_walk.cuh; replaces the reference's random_device-seeded mt19937,
+ * /root/reference/include/mccompletepathv2.h:32-34). */
+int pprb200_debug_philox(const uint32_t* ctr_key, uint32_t* out, int32_t nblocks);
 
 /* Quality-evaluator yardstick: exact Personalized PageRank by power iteration for a batch of
  * sources -- replaces ppr::pprInternal::pprSingleSource (/root/reference/include/internal/pprSingleSource.h:28-75)

@@ -20,6 +20,22 @@
 #include <unordered_set>
 #include <vector>
 
+// A second key type with a different std::hash: the same graph iterates in another order, so partitions, summation
+// order and every boundary tie may fall differently -- the reference's self-noise band (SURVEY.md 7-1, App. B rmat_probe).
+struct AltKey {
+  int v;
+  bool operator==(const AltKey& o) const { return v == o.v; }
+};
+namespace std {
+template <>
+struct hash<AltKey> {
+  size_t operator()(const AltKey& k) const {
+    unsigned long long x = (unsigned long long)(unsigned int)k.v * 0x9E3779B97F4A7C15ull;
+    return (size_t)(x ^ (x >> 29));
+  }
+};
+}  // namespace std
+
 #include <grank.h>             // /root/reference/include/grank.h
 #include <grankMulti.h>        // /root/reference/header-only/grankMulti.h
 #include <mccompletepathv2.h>  // /root/reference/include/mccompletepathv2.h
@@ -82,6 +98,29 @@ int ref_grank(const int64_t* row_ptr, const int32_t* col, int32_t n, uint32_t K,
   auto t1 = std::chrono::steady_clock::now();
   if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
   if (out_ids) flatten(res, n, K, out_ids, out_scores, out_cnt);
+  return 0;
+}
+
+// grank.h:42-150 instantiated for AltKey (same graph, same parameters, different hash order)
+int ref_grank_althash(const int64_t* row_ptr, const int32_t* col, int32_t n, uint32_t K, uint32_t L, uint32_t iterations,
+                      double damping, double tolerance, int32_t* out_ids, double* out_scores, uint32_t* out_cnt) {
+  std::unordered_map<AltKey, std::vector<AltKey>> g;
+  for (int32_t v = 0; v < n; v++) {
+    std::vector<AltKey>& s = g[AltKey{v}];
+    for (int64_t i = row_ptr[v]; i < row_ptr[v + 1]; i++) s.push_back(AltKey{col[i]});
+  }
+  auto res = ppr::grank<AltKey>(g, K, L, iterations, damping, tolerance);
+  for (int32_t v = 0; v < n; v++) {
+    uint32_t c = 0;
+    auto it = res.find(AltKey{v});
+    if (it != res.end())
+      for (const auto& kv : it->second) {
+        if (c < K) { out_ids[(size_t)v * K + c] = kv.first.v; out_scores[(size_t)v * K + c] = kv.second; }
+        c++;
+      }
+    out_cnt[v] = c;
+    for (uint32_t i = c; i < K; i++) { out_ids[(size_t)v * K + i] = -1; out_scores[(size_t)v * K + i] = 0.0; }
+  }
   return 0;
 }
 

@@ -142,6 +142,15 @@ def ref_grank(g, K, L, iterations, damping, tolerance, nthreads=None):
     return Result(ids, sc, cnt[:g.n], None, sec.value)
 
 
+def ref_grank_althash(g, K, L, iterations, damping, tolerance):
+    """the unmodified ppr::grank on the same graph under a different std::hash (the reference's self-noise probe)"""
+    ids, sc, cnt = _outs(g.n, K)
+    ref().ref_grank_althash(P(g.row_ptr), P(g.col), C.c_int32(g.n), C.c_uint32(K), C.c_uint32(L), C.c_uint32(iterations),
+                            C.c_double(damping), C.c_double(tolerance), P(ids), P(sc), P(cnt))
+    ids, sc = _sorted_rows(ids[:g.n], sc[:g.n], cnt[:g.n])
+    return Result(ids, sc, cnt[:g.n])
+
+
 def ref_mc(g, K, L, R, damping):
     ids, sc, cnt = _outs(g.n, K)
     sec = C.c_double(0)

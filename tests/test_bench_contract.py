@@ -14,7 +14,8 @@ import oracle_bindings as ob  # noqa: E402
 
 @pytest.mark.skipif(not ob.have_ref(), reason="needs oracle/_ref (the reference build)")
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
-    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    # (the default workload, R-MAT-22, takes minutes on the CPU test box: the contract is checked on BASELINE configs[1])
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--workload", "rmat16"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
@@ -26,6 +27,21 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["reference_sample"] == "full job"  # R-MAT-16: all 30 iterations, nothing extrapolated
+    # the reference process never maps the product library (its graph comes from the numpy generator)
+    assert "libppr_b200" not in r.stderr
+
+
+def test_default_workload_is_the_configuration_the_target_is_quoted_on():
+    """BENCH / SCALE measure GRank on R-MAT scale 22 (BASELINE configs[3]) with the MC R-MAT-20 job under "mc"; big graphs
+    bound the reference arm to one sweep of each partition, labelled as extrapolated"""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert bench.DEFAULT_WORKLOAD == "rmat22"
+    w = bench.WORKLOADS[bench.DEFAULT_WORKLOAD]
+    assert w["kind"] == "grank" and w["scale"] == 22 and (w["K"], w["L"], w["iterations"]) == (50, 100, 30)
+    assert bench.WORKLOADS["rmat20mc"]["kind"] == "mc" and bench.WORKLOADS["rmat20mc"]["iterations"] == 1000
+    assert bench.REFERENCE_SAMPLE_ITERATIONS == 2 and (1 << 22) > bench.REFERENCE_FULL_JOB_NODES
 
 
 def test_b200_arm_fails_loudly_without_a_gpu():

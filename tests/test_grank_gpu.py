@@ -34,6 +34,22 @@ def assert_same_stats(got, want):
 
 
 @pytest.mark.parametrize("name", golden_cases("grank"))
+def test_golden_reference_vectors_default_configuration(name):
+    """the configuration bench.py times (hub_threshold = 0: order-free above out-degree 12) against the unmodified reference's
+    output on the tie-free fixtures -- several have out-degrees far above 12 (random100_5000, complete100, rmat10_k50_l2000):
+    identical membership, |d| <= 1e-9 (the fixed-point sums differ from the fma chain by <= outdeg * 2^-62)"""
+    g, z = load_golden(name)
+    order = z["order"]
+    got = ppr.grank_csr(g.relabel(order), int(z["K"]), int(z["L"]), int(z["iterations"]), float(z["damping"]), float(z["tolerance"]),
+                        colour=None, hub_threshold=0)
+    gk = ob.baskets_to_keyspace(got, order)
+    assert (gk.cnt == np.minimum(z["cnt"], int(z["K"]))).all()
+    mism, maxd = compare_membership(gk, ob.Result(z["ids"], z["scores"], z["cnt"]))
+    assert mism == 0
+    assert maxd <= TOL
+
+
+@pytest.mark.parametrize("name", golden_cases("grank"))
 def test_golden_reference_vectors(name):
     """GPU vs the unmodified reference's output (tie-free fixtures): identical membership, |d| <= 1e-9"""
     g, z = load_golden(name)

@@ -18,6 +18,10 @@ for rep in range(2):
     st = s.stats(); l, ms = s.kernel_time(0)
     print(f"rmat{scale} hub>{hub} dense={dense}: kernel_ms {st['kernel_ms']:.2f} merge_ms {ms:.2f} ({ms/iters:.2f}/iteration) alg GB/s {st['algorithmic_bytes']/ms/1e6:.1f} "
           f"frac {st['algorithmic_bytes']/ms/1e6/6543.1:.3f} requeues {st['overflow_requeues']} merged {st['merged_entries']}")
+    if dense:
+        d = (C.c_ulonglong * 8)()
+        lib.pprb200_debug_counters(s.handle, d)
+        print("  dense kernels: nodes done %d, ran pass 2 %d, tau=0 %d; handed over: untrusted %d, candidates>CMAX %d, tail full %d, split-hub items %d" % tuple(d[i] for i in range(7)))
     buf = np.zeros(2 * 148 * 8 * 8, dtype=np.uint64); n = C.c_int(0)
     lib.pprb200_debug_prof(s.handle, buf.ctypes.data_as(C.c_void_p), C.byref(n))
     buf = buf.reshape(2, 148 * 8, 8)

@@ -8,4 +8,6 @@ s = ppr.Session(g, 100, colour=col)
 for r in range(reps):
     s.grank(50, 100, iters, 0.85, -1.0)
     st = s.stats(); l, ms = s.kernel_time(0)
+    import os
+    print({k: v for k, v in os.environ.items() if k.startswith('PPRB200')}, end=' ')
     print(f"rmat{scale} it={iters}: kernel_ms {st['kernel_ms']:.2f} merge_ms {ms:.2f} frac {st['algorithmic_bytes']/ms/1e6/6543.1:.4f} requeues {st['overflow_requeues']}")
