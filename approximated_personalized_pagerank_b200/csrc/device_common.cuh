@@ -48,7 +48,8 @@ struct RunState {
   int peer_timeout;          // set when a cross-GPU barrier gave up waiting
   unsigned long long barrier_seq;  // executed cross-GPU barriers (kept across runs)
   // merge_dense_kernel bookkeeping (pprb200_debug_counters): nodes finished, nodes that ran pass 2, nodes with tau = 0,
-  // hand-overs by reason (untrusted contribution, candidates > CMAX, tail table full), split-hub items passed on
+  // hand-overs by reason (untrusted contribution, candidates > CMAX, tail table full), split-hub items passed on,
+  // nodes handed over unread because their old basket was not full
   unsigned long long dbg[8];
 };
 

@@ -214,6 +214,14 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
       if (cntv >= L) theta0 = __longlong_as_double((long long)mn);
     }
     const int npre = S->tcount;  // (block_reduce_min_sum ends with a barrier)
+    if (theta0 == 0.0) {
+      // the old basket is not full yet (the first update of a low-degree node): nothing bounds the cut, every label would be
+      // a candidate -- the general kernel's job; hand the node over before reading a single successor basket
+      __syncthreads();
+      for (int i = tid; i < npre; i += THREADS) { const int s2 = t_list[i]; t_keys[s2] = KEY_EMPTY; }
+      if (tid == 0) { P.fb_queue[atomicAdd(&st->qcount[P.fb_idx], 1u)] = (unsigned int)P.item_base + item; s_requeue++; dbg[7]++; S->tcount = 0; }
+      continue;
+    }
     bool bad = false;            // this thread saw a contribution that must not be trusted
     if (tid == 0) {              // the self term (grank.h:101 / mccompletepathv2.h:226)
       bad |= contribute(self_id, xself);

@@ -237,7 +237,7 @@ struct pprb200_session {
   unsigned char* d_buf[2] = {nullptr, nullptr};
   size_t buf_bytes = 0;
   unsigned int* d_queue[4] = {nullptr, nullptr, nullptr, nullptr};
-  unsigned int* d_fb_queue = nullptr;  // [n_items] items merge_dense hands over to merge_par
+  unsigned int* d_fb_queue = nullptr;  // [2 * n_items] items merge_dense hands over to merge_par: mid class | big class
   int* d_ncand = nullptr;
   RunState* d_state = nullptr;
   unsigned long long* d_final_stats = nullptr;
@@ -670,6 +670,9 @@ static int session_from_plan(const HostPlan& H, const RankPlan& R, uint32_t max_
     s->tbl_cap[0] = std::min(s->tbl_cap[1], pow2cap((unsigned long long)s->mid_deg));
     s->tbl_count_cls[1] = s->sm_count + 8;      // >= CTAs in flight of the big instantiation
     s->tbl_count_cls[0] = s->sm_count * 3 + 8;  // ... of the mid instantiation
+    // merge_dense_kernel in front: merge_par only sees the init pass (multiplicities: small tables), split hubs and the
+    // few hand-overs -- 64 tables are plenty (a CTA that finds none free waits for one), and 68 GB of pool become 28
+    if (dense_enabled()) s->tbl_count_cls[1] = 64;
     s->tbl_first[1] = 0;
     s->tbl_first[0] = s->tbl_count_cls[1];
     s->pool_off[1] = 0;
@@ -680,7 +683,7 @@ static int session_from_plan(const HostPlan& H, const RankPlan& R, uint32_t max_
         (rc = dev_alloc(&s->d_item_len, (size_t)s->n_items)) || (rc = dev_alloc(&s->d_pool, pool_bytes)) ||
         (rc = dev_alloc(&s->d_tbl_inuse, (size_t)n_tables)) || (rc = dev_alloc(&s->d_tbl_count, (size_t)n_tables)) ||
         (rc = dev_alloc(&s->d_node_tbl, (size_t)M)) || (rc = dev_alloc(&s->d_node_done, (size_t)M)) ||
-        (rc = dev_alloc(&s->d_fb_queue, (size_t)s->n_items))) {
+        (rc = dev_alloc(&s->d_fb_queue, (size_t)2 * s->n_items))) {
       session_free(s);
       return rc;
     }
@@ -874,7 +877,7 @@ static cudaError_t launch_par(pprb200_session* s, const ParParams& P, int grid) 
 }
 
 template <int H, int R, int TCAP, int CMAX, int COLCAP, int THREADS, int MINB>
-static cudaError_t launch_dense(pprb200_session* s, const DenseParams& P, int grid) {
+static cudaError_t launch_dense(pprb200_session* s, const DenseParams& P, int per_sm) {
   const size_t smem = dense_smem_bytes<H, R, TCAP, CMAX, COLCAP>();
   static bool configured[64] = {false};
   if (!configured[s->device & 63]) {
@@ -882,7 +885,7 @@ static cudaError_t launch_dense(pprb200_session* s, const DenseParams& P, int gr
     if (e != cudaSuccess) return e;
     configured[s->device & 63] = true;
   }
-  merge_dense_kernel<H, R, TCAP, CMAX, COLCAP, THREADS, MINB><<<grid, THREADS, smem, s->cur>>>(P);
+  merge_dense_kernel<H, R, TCAP, CMAX, COLCAP, THREADS, MINB><<<std::min(s->sm_count * per_sm, P.n_items), THREADS, smem, s->cur>>>(P);
   s->launch_count++;
   return cudaGetLastError();
 }
@@ -945,26 +948,26 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
       D.item_base = b + n_hub;
       D.chunk = s->chunk;
       D.work_idx = 8 + cls;
-      D.fb_queue = s->d_fb_queue;
-      D.fb_idx = 4;
+      D.fb_queue = s->d_fb_queue + (size_t)cls * s->n_items;  // each class hands over to its own merge_par instantiation
+      D.fb_idx = 4 + cls;
       D.prof = s->d_prof ? s->d_prof + (size_t)cls * s->sm_count * 8 * 8 : nullptr;
       s->cur = cls == 0 ? side : s->stream;
       cudaError_t err;
-      if (cls == 1)
-        err = s->dense_threads == 512 ? launch_dense<8192, 16384, 2048, 2048, 1024, 512, 1>(s, D, std::min(s->sm_count, D.n_items))
-                                      : launch_dense<8192, 16384, 2048, 2048, 1024, 1024, 1>(s, D, std::min(s->sm_count, D.n_items));
-      else {
+      if (cls == 1) {
+        err = s->dense_threads == 512 ? launch_dense<8192, 16384, 4096, 2048, 1024, 512, 1>(s, D, 1)
+                                      : launch_dense<8192, 16384, 4096, 2048, 1024, 1024, 1>(s, D, 1);
+      } else {
         static const int cfg = getenv("PPRB200_MID_CFG") ? atoi(getenv("PPRB200_MID_CFG")) : 0;  // A/B hook
-        if (cfg == 1) err = launch_dense<2048, 4096, 512, 512, PAR_MID_MAX, 128, 4>(s, D, std::min(s->sm_count * 4, D.n_items));
-        else if (cfg == 2) err = launch_dense<1024, 8192, 512, 512, PAR_MID_MAX, 128, 4>(s, D, std::min(s->sm_count * 4, D.n_items));
-        else if (cfg == 3) err = launch_dense<2048, 8192, 1024, 512, PAR_MID_MAX, 256, 3>(s, D, std::min(s->sm_count * 3, D.n_items));
-        else err = launch_dense<4096, 8192, 2048, 1024, PAR_MID_MAX, 512, 2>(s, D, std::min(s->sm_count * 2, D.n_items));
+        if (cfg == 3) err = launch_dense<2048, 8192, 1024, 512, PAR_MID_MAX, 256, 3>(s, D, 3);
+        else if (cfg == 2) err = launch_dense<4096, 8192, 2048, 1024, PAR_MID_MAX, 512, 2>(s, D, 2);
+        else err = launch_dense<1024, 4096, 512, 512, PAR_MID_MAX, 128, 5>(s, D, 5);
       }
       if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_dense launch failed: %s", cudaGetErrorString(err));
     }
   }
   if (dense && s->item_end[c][1] > s->item_begin[c][0]) {
-    // whatever the dense kernels handed over (in practice a few nodes of the first iterations): merge_par from the queue
+    // whatever the dense kernels handed over (first updates of low-degree nodes, a few overflows): merge_par from the queues,
+    // the mid class on its 128-thread instantiation (three CTAs per SM), the big class on the 512-thread one
     if (s->overlap) {
       cudaEventRecord(s->ev_join[0], side);
       cudaStreamWaitEvent(s->stream, s->ev_join[0], 0);
@@ -973,14 +976,18 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
     P.item_begin = s->d_item_off;
     P.item_len = s->d_item_len;
     P.n_items = 0;
-    P.item_queue = s->d_fb_queue;
-    P.queue_idx = 4;
-    P.work_idx = 10;
-    par_class(1);
     P.prof = nullptr;
     s->cur = s->stream;
-    cudaError_t err = launch_par<8192, 2048, 3072, PAR_CHUNK_MAX, 8192, 512>(s, P, s->sm_count);
-    if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_par (hand-over queue) launch failed: %s", cudaGetErrorString(err));
+    for (int cls = 1; cls >= 0; cls--) {
+      if (s->item_end[c][cls] == s->item_begin[c][cls]) continue;
+      P.item_queue = s->d_fb_queue + (size_t)cls * s->n_items;
+      P.queue_idx = 4 + cls;
+      P.work_idx = 10 + cls;
+      par_class(cls);
+      cudaError_t err = cls == 1 ? launch_par<8192, 2048, 3072, PAR_CHUNK_MAX, 8192, 512>(s, P, std::min(s->sm_count, s->tbl_count_cls[1]))
+                                 : launch_par<2048, 2048, 2048, PAR_MID_MAX, 0, 128>(s, P, s->sm_count * 3);
+      if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_par (hand-over queue) launch failed: %s", cudaGetErrorString(err));
+    }
   }
   s->cur = s->stream;
   return PPRB200_OK;
@@ -1424,6 +1431,19 @@ static long long peer_timeout_cycles() {
   return (long long)(ms * 2.0e6);
 }
 
+// hand the stream-ordered allocator's cached blocks of the current device back to the driver (sessions keep freed memory in the
+// pool for the next call: another process that wants the GPU's memory asks for this first)
+int pprb200_release_cached_memory(void) {
+  std::lock_guard<std::mutex> lk(g_api_mutex);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return PPRB200_OK; }
+  cudaDeviceSynchronize();
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+  cudaGetLastError();
+  return PPRB200_OK;
+}
+
 // debug: out[i][4] = Philox4x32-10(counter = ctr_key[i][0..3], key = ctr_key[i][4..5]) computed by the device function of mc_walk.cuh
 int pprb200_debug_philox(const uint32_t* ctr_key, uint32_t* out, int32_t nblocks) {
   if (!ctr_key || !out || nblocks <= 0) return fail(PPRB200_ERR_PARAM, "bad argument");
@@ -1493,6 +1513,43 @@ int pprb200_session_ipc_attach(pprb200_session* s, const void* all_handles) {
   }
   s->peers = pd;
   s->attached = true;
+  return PPRB200_OK;
+}
+
+// same wiring for sessions that live in ONE process (one per device, or -- tests -- several on one device): plain peer
+// pointers instead of IPC handles. all[r] = the session of rank r; every session gets the same view.
+int pprb200_session_attach_local(pprb200_session** all, int32_t world) {
+  if (!all || world < 1 || world > MAX_WORLD) return fail(PPRB200_ERR_PARAM, "bad argument");
+  std::lock_guard<std::mutex> lk(g_api_mutex);
+  for (int r = 0; r < world; r++)
+    if (!all[r] || all[r]->world != world || all[r]->rank != r || all[r]->attached)
+      return fail(PPRB200_ERR_STATE, "session %d is not an unattached rank %d of %d", r, r, world);
+  int dev0 = 0;
+  cudaGetDevice(&dev0);
+  for (int a = 0; a < world; a++)
+    for (int b2 = 0; b2 < world; b2++) {
+      if (all[a]->device == all[b2]->device) continue;
+      cudaSetDevice(all[a]->device);
+      const cudaError_t e = cudaDeviceEnablePeerAccess(all[b2]->device, 0);
+      cudaGetLastError();
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        cudaSetDevice(dev0);
+        return fail(PPRB200_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", all[a]->device, all[b2]->device, cudaGetErrorString(e));
+      }
+    }
+  for (int r = 0; r < world; r++) {
+    PeerDev pd;
+    std::memset(&pd, 0, sizeof(pd));
+    pd.world = world;
+    pd.rank = r;
+    pd.timeout_cycles = peer_timeout_cycles();
+    for (int q = 0; q < world; q++) { pd.buf[q][0] = all[q]->d_buf[0]; pd.buf[q][1] = all[q]->d_buf[1]; pd.mbox[q] = all[q]->d_mbox; }
+    cudaSetDevice(all[r]->device);
+    cudaStreamSynchronize(all[r]->stream);  // mailbox zeroed before anybody posts
+    all[r]->peers = pd;
+    all[r]->attached = true;
+  }
+  cudaSetDevice(dev0);
   return PPRB200_OK;
 }
 

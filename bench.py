@@ -327,7 +327,7 @@ def run_job(w, wname, args, cx, steps, warm, hub_threshold, want_e2e=True, want_
     e2e = None
     e_steps = max(1, min(steps, 3))
     n, K = g.n, w["K"]
-    if want_e2e and (world == 1 or rank == 0 or not cx.inproc_multi):
+    if want_e2e and (world == 1 or rank == 0):
         import ctypes as C
         pin = lambda a: torch.from_numpy(a).pin_memory().numpy()  # noqa: E731
         ids = torch.empty((n, K), dtype=torch.int32).pin_memory().numpy()
@@ -359,41 +359,45 @@ def run_job(w, wname, args, cx, steps, warm, hub_threshold, want_e2e=True, want_
                "ms_per_step": 1e3 * sec / e_steps, "host_prep_ms": st.prep_ms, "kernel_ms": st.kernel_ms, "d2h_ms": st.d2h_ms,
                "api": "pprb200_grank / pprb200_mccompletepathv2 (one-shot C-ABI, host CSR in, flat baskets out)"}
     elif want_e2e:
-        # N GPUs end to end through the public multi-GPU API: every rank preprocesses + uploads the CSR from host memory,
-        # the ranks exchange IPC handles, run, and rank 0 reads the whole result back
-        from approximated_personalized_pagerank_b200 import multigpu
+        # N GPUs end to end through the same one-shot C-ABI call: PPR_NUM_GPUS = N makes rank 0's process plan once and drive
+        # all N devices itself (a session per device, peer access); the other ranks' processes only wait here
+        sess.close()
+        sess = None
+        torch.cuda.empty_cache()
+        lib.pprb200_release_cached_memory()
+        barrier()
+        if rank == 0:
+            os.environ["PPR_NUM_GPUS"] = str(world)
+            rp, cl = pin(g.row_ptr), pin(g.col)
+            st = _lib.Stats()
 
-        def e2e_multi():
-            s2 = ppr.Session(g, w["L"], colour=None if w["kind"] == "grank" else np.zeros(n, dtype=np.uint8),
-                             hub_threshold=hub_threshold, rank=rank, world=world, stream=stream.cuda_stream)
-            multigpu.connect(s2, dist)
-            if w["kind"] == "grank":
-                s2.grank(K, w["L"], w["iterations"], w["damping"], w["tolerance"])
-            else:
-                s2.mc(K, w["L"], w["iterations"], w["damping"])
-            if rank == 0:
-                s2.fetch(ids, sc, cnt)
-            st2 = s2.stats()
-            torch.cuda.synchronize()
-            dist.barrier()
-            s2.close()
-            return st2["node_iterations"] if w["kind"] == "grank" else st2["walk_steps"]
-        e2e_multi()
+            def e2e_step():
+                if w["kind"] == "grank":
+                    _lib.check(lib.pprb200_grank(_lib.ptr(rp), _lib.ptr(cl), n, None, K, w["L"], w["iterations"], w["damping"],
+                                                 w["tolerance"], hub_threshold, _lib.ptr(ids), _lib.ptr(sc), _lib.ptr(cnt), C.byref(st)))
+                    return st.node_iterations
+                _lib.check(lib.pprb200_mccompletepathv2(_lib.ptr(rp), _lib.ptr(cl), n, K, w["L"], w["iterations"], w["damping"],
+                                                        ppr.api.DEFAULT_MC_SEED, ppr.api.DEFAULT_MC_ROUNDS, hub_threshold,
+                                                        _lib.ptr(ids), _lib.ptr(sc), _lib.ptr(cnt), C.byref(st)))
+                return st.walk_steps
+            e2e_step()
+            t0 = time.perf_counter()
+            u = 0
+            for _ in range(e_steps):
+                u += e2e_step()
+            sec = time.perf_counter() - t0
+            lib.pprb200_release_cached_memory()
+            os.environ["PPR_NUM_GPUS"] = "1"
+            e2e = {"value": u / sec, "unit": unit, "h2d_bytes_per_step": int(world * (g.row_ptr.nbytes + g.col.nbytes + g.n * 5)),
+                   "d2h_bytes_per_step": int(n * K * 12 + n * 4), "ms_per_step": 1e3 * sec / e_steps, "n_gpus_used": int(st.n_gpus),
+                   "host_prep_ms": st.prep_ms, "kernel_ms": st.kernel_ms, "d2h_ms": st.d2h_ms,
+                   "api": f"pprb200_grank / pprb200_mccompletepathv2 with PPR_NUM_GPUS={world}: one process, one host plan, a session per device over peer access"}
         barrier()
-        t0 = time.perf_counter()
-        u = sum(e2e_multi() for _ in range(e_steps))
-        barrier()
-        sec = time.perf_counter() - t0
-        tu = torch.tensor([u if w["kind"] == "mc" else 0], dtype=torch.int64, device="cuda")
-        dist.all_reduce(tu)
-        u = int(tu[0]) if w["kind"] == "mc" else u
-        e2e = {"value": u / sec, "unit": unit, "h2d_bytes_per_step": int(world * (g.row_ptr.nbytes + g.col.nbytes + g.n * 5)),
-               "d2h_bytes_per_step": int(n * K * 12 + n * 4), "ms_per_step": 1e3 * sec / e_steps,
-               "api": "Session(rank, world) per process + multigpu.connect (CUDA IPC) + fetch on rank 0"}
 
     if world > 1:
         dist.barrier()
-    sess.close()
+    if sess is not None:
+        sess.close()
     if rank != 0:
         return None
     peak, peak_src = measured_peak()
@@ -505,7 +509,7 @@ def main():
     default = args.workload == DEFAULT_WORKLOAD
     if default and not args.no_exact and args.hub_threshold == 0:
         # the same job with the reference's exact fma order for every node (bit-identical to the reference's arithmetic)
-        ex = run_job(w, args.workload, args, cx, 1, 1, NEVER_HUB, want_e2e=False, want_cpu=False, sample_clocks=False)
+        ex = run_job(w, args.workload, args, cx, 1, 0, NEVER_HUB, want_e2e=False, want_cpu=False, sample_clocks=False)
         if line is not None and ex is not None:
             line["exact_order"] = {k: ex[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "gpu_launches")}
             line["exact_order"]["roofline_frac"] = ex["roofline"]["frac"]
@@ -521,6 +525,9 @@ def main():
     if cx.rank != 0 or line is None:
         return
     if cx.world == 1 and not args.no_e2e:
+        del cx.flush
+        torch.cuda.empty_cache()
+        cx.lib.pprb200_release_cached_memory()  # the C++ program below is another process: give it the GPU's memory
         line["e2e_api"] = e2e_api_cpp(args.workload)
     try:
         line["parity_report"] = json.loads((ROOT / "profiles" / "r2" / "parity_report.json").read_text())

@@ -134,10 +134,17 @@ int pprb200_session_kernel_time(pprb200_session* s, int which, uint32_t* launche
 #define PPRB200_MAX_WORLD 8
 int pprb200_session_ipc_export(pprb200_session* s, void* out /* PPRB200_IPC_BYTES */);
 int pprb200_session_ipc_attach(pprb200_session* s, const void* all_handles /* world * PPRB200_IPC_BYTES */);
+/* The same wiring for the ranks of one job that live in ONE process (a session per device): plain peer pointers, no IPC.
+ * all[r] = the unattached session of rank r, r = 0..world-1. (The one-shot entry points do this themselves: PPR_NUM_GPUS.) */
+int pprb200_session_attach_local(pprb200_session** all, int32_t world);
 /* owner[v] = rank that updates node v in a world-rank session (-1 for sinks: nobody). Host only. colour may be
  * NULL (MC sessions: one class). */
 int pprb200_shard_owner(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour, uint32_t hub_threshold,
                         int32_t world, int32_t* owner);
+
+/* Device memory freed by destroyed sessions stays cached in the stream-ordered pool for the next call; this returns it to the
+ * driver (e.g. before another process needs the GPU). */
+int pprb200_release_cached_memory(void);
 
 /* Kernels the last run enqueued on the session stream (bench.py's gpu_launches). */
 int pprb200_session_launches(pprb200_session* s, uint64_t* launches);

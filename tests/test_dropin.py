@@ -149,3 +149,47 @@ def test_evaluator_dropin_reports_the_reference_statistics():
     if EVAL_REF.exists():
         q = run(EVAL_REF)
         assert q.returncode == 0 and _eval_lines(q.stdout) == want
+
+
+# ---- the reference's demo (src/main.cc:30-76) on its own dataset, against both header sets ---------------
+def _demo_stats(text):
+    """{'grank multi': {'average jaccard': .., 'average kendall': .., ...}, 'grank': {...}, 'mc': {...}} from the demo's output"""
+    out, cur = {}, None
+    for ln in text.splitlines():
+        if ln.endswith(" ms") and " run-time = " in ln:
+            cur = ln.split(" run-time = ")[0]
+            out[cur] = {"ms": float(ln.split(" run-time = ")[1].split()[0])}
+        elif cur and "     " in ln:
+            k, v = ln.rsplit("     ", 1)
+            try:
+                out[cur][k.strip()] = float(v)
+            except ValueError:
+                pass
+    return out
+
+
+@pytest.mark.gpu
+def test_demo_program_on_the_reference_dataset_matches_the_reference_build(tmp_path):
+    """examples/demo_main.cc -- the reference's demo with its own parameters (grankMulti(50,100,30,0.85,1e-4,4), grank(...),
+    mccompletepathv2(50,200,1000,0.85)) -- built against the drop-in headers, run on the reference's example.txt
+    (tests/golden/example_edges.csv.gz: 23 132 nodes, 312 310 edges). tests/golden/demo_reference.txt is the same program built
+    against the UNMODIFIED reference headers (tests/golden/make_demo_golden.sh). Both sample 200 random sources, so the
+    averages agree within sampling noise: Jaccard / Kendall averages within 0.03."""
+    import gzip
+    root = Path(__file__).resolve().parent.parent
+    exe = root / "tests" / "cpp" / "demo_main_b200"
+    gold = root / "tests" / "golden" / "demo_reference.txt"
+    data = root / "tests" / "golden" / "example_edges.csv.gz"
+    if not (exe.exists() and gold.exists() and data.exists()):
+        pytest.skip("demo binary / golden / dataset fixture missing")
+    csv = tmp_path / "example.txt"
+    csv.write_bytes(gzip.open(data, "rb").read())
+    r = subprocess.run([str(exe), str(csv)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got, want = _demo_stats(r.stdout), _demo_stats(gold.read_text())
+    assert r.stdout.splitlines()[0] == gold.read_text().splitlines()[0]  # "nodes: 23132 edges: 312310": same ingest (dedup, sinks)
+    for algo in ("grank multi", "grank", "mc"):
+        for k in ("jaccard average", "kendall average"):
+            assert abs(got[algo][k] - want[algo][k]) <= 0.03, (algo, k, got[algo][k], want[algo][k])
+        assert got[algo]["average map size"] == want[algo]["average map size"]
+        print(algo, {k: (got[algo].get(k), want[algo].get(k)) for k in want[algo]})

@@ -72,11 +72,82 @@ def test_multi_rank_session_refuses_to_run_before_attach():
 
 
 @pytest.mark.gpu
-def test_two_gpus_bit_identical_to_the_oracle():
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_n_gpus_bit_identical_to_the_oracle(world):
+    """one process per GPU (torchrun): every rank ends with the same baskets, bit-identical to the single-process oracle --
+    GRank and MCCompletePathV2 do not depend on the GPU count (skipped by device count: `gpurun --gpus N`)"""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                        "--master-port", str(29611 + world), str(ROOT / "tests" / "multigpu_worker.py"), "12"], capture_output=True, text=True,
+                       timeout=1200)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_one_process_multi_gpu_behind_the_one_shot_c_abi(world, monkeypatch):
+    """PPR_NUM_GPUS: pprb200_grank / pprb200_mccompletepathv2 shard the sources over N devices inside ONE
+    process -- peer access, no IPC, same kernels -- and return the same bits as on one GPU and as the oracle."""
+    import torch
+    import oracle_bindings as ob
+    from helpers import assert_bit_identical
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
+    g = G.rmat(13)
+    colour = ppr.find_partitions_csr(g)
+    monkeypatch.setenv("PPR_NUM_GPUS", str(world))
+    got = ppr.grank_csr(g, 50, 100, 12, 0.85, 1e-3, colour=colour)
+    assert got.stats["n_gpus"] == world
+    want = ob.oracle_grank(g, 50, 100, 12, 0.85, 1e-3, colour=colour, hub_threshold=ppr.DEFAULT_HUB_THRESHOLD)
+    assert_bit_identical(got, want, f"one process, {world} GPUs, grank")
+    for k in ("iterations_run", "merged_entries", "nonsink_node_iterations", "truncations", "boundary_ties"):
+        assert got.stats[k] == want.stats[k], (k, got.stats[k], want.stats[k])
+    mc = ppr.mccompletepathv2_csr(g, 50, 100, 200, 0.85)
+    assert mc.stats["n_gpus"] == world
+    wmc = ob.oracle_mc(g, 50, 100, 200, 0.85, ppr.api.DEFAULT_MC_SEED, ppr.api.DEFAULT_MC_ROUNDS, hub_threshold=ppr.DEFAULT_HUB_THRESHOLD)
+    assert_bit_identical(mc, wmc, f"one process, {world} GPUs, mc")
+    assert mc.stats["walk_steps"] == wmc.stats["walk_steps"]
+    monkeypatch.setenv("PPR_NUM_GPUS", "1")
+    one = ppr.grank_csr(g, 50, 100, 12, 0.85, 1e-3, colour=colour)
+    assert one.stats["n_gpus"] == 1
+    assert_bit_identical(got, one, "N GPUs vs one GPU")
+
+
+@pytest.mark.gpu
+def test_drop_in_cpp_program_on_two_gpus_equals_one_gpu():
+    """the unchanged template API (ppr::grank on an unordered_map) reaches the multi-GPU path through PPR_NUM_GPUS: the
+    drop-in check program prints the same baskets with 2 GPUs as with 1"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29611", str(ROOT / "tests" / "multigpu_worker.py"), "12"], capture_output=True, text=True,
-                       timeout=900)
-    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    exe = ROOT / "tests" / "cpp" / "dropin_check_b200"
+    if not exe.exists():
+        pytest.skip("tests/cpp/dropin_check_b200 not built")
+    outs = []
+    for n in ("1", "2"):
+        r = subprocess.run([str(exe), "random_full"], capture_output=True, text=True, timeout=600, env=dict(os.environ, PPR_NUM_GPUS=n))
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout)
+    assert outs[0] == outs[1] and len(outs[0]) > 100
+
+
+@pytest.mark.gpu
+def test_a_peer_that_never_attaches_is_reported_not_ignored(monkeypatch):
+    """world = 2 session whose peer never runs: the mailbox barrier gives up after PPRB200_PEER_TIMEOUT_MS, the run stops, and
+    stats / fetch return PPRB200_ERR_CUDA instead of PPRB200_OK with garbage (both ranks' sessions live on the one GPU of the
+    test box and are wired with pprb200_session_attach_local; only rank 0 ever runs)"""
+    from approximated_personalized_pagerank_b200 import _lib
+    monkeypatch.setenv("PPRB200_PEER_TIMEOUT_MS", "200")
+    import ctypes as C
+    g = G.rmat(9)
+    s = ppr.Session(g, 100, rank=0, world=2)
+    s2 = ppr.Session(g, 100, rank=1, world=2)   # the "peer": attached, but its run is never enqueued
+    arr = (C.c_void_p * 2)(s.handle, s2.handle)
+    _lib.check(s.lib.pprb200_session_attach_local(arr, 2))
+    s.grank(10, 20, 4, 0.85, -1.0)   # rank 1 never runs: rank 0's first barrier times out
+    with pytest.raises(_lib.PprB200Error, match="peer barrier timed out"):
+        s.stats()
+    with pytest.raises(_lib.PprB200Error, match="peer barrier timed out"):
+        s.fetch()

@@ -21,7 +21,7 @@ for rep in range(2):
     if dense:
         d = (C.c_ulonglong * 8)()
         lib.pprb200_debug_counters(s.handle, d)
-        print("  dense kernels: nodes done %d, ran pass 2 %d, tau=0 %d; handed over: untrusted %d, candidates>CMAX %d, tail full %d, split-hub items %d" % tuple(d[i] for i in range(7)))
+        print("  dense kernels: nodes done %d, ran pass 2 %d, tau=0 %d; handed over: untrusted %d, candidates>CMAX %d, tail full %d, split-hub items %d, old basket not full %d" % tuple(d[i] for i in range(8)))
     buf = np.zeros(2 * 148 * 8 * 8, dtype=np.uint64); n = C.c_int(0)
     lib.pprb200_debug_prof(s.handle, buf.ctypes.data_as(C.c_void_p), C.byref(n))
     buf = buf.reshape(2, 148 * 8, 8)
