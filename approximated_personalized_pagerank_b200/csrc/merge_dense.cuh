@@ -355,12 +355,13 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
     sweep(1);
     DPROF_MARK(1);
     bool bail = __syncthreads_or(bad ? 1 : 0) != 0;  // (also: pass 1 complete)
-    dbg[3] += bail;
+    (void)bail;
 
     // ---- exact candidates (dense + pre labels) -> compact (score bits, label) arrays ----
     // scan 1 counts how many reach theta0, 3/4, 1/2, 1/16 of it: tau = the highest level that L of them reach is a lower
     // bound of the cut (0 when none is); scan 2 compacts the candidates >= tau.
     bool dropped_local = false;  // this thread saw a candidate that is not in the compact arrays
+    bool wide = false;           // more candidates than the compact arrays hold: select / write address the tables themselves
     double tau = 0.0;
     int n = 0;
     if (!bail) {
@@ -368,8 +369,13 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
         const unsigned long long l0 = (unsigned long long)__double_as_longlong(theta0), l1 = (unsigned long long)__double_as_longlong(theta0 * 0.75),
                                  l2 = (unsigned long long)__double_as_longlong(theta0 * 0.5), l3 = (unsigned long long)__double_as_longlong(theta0 * 0.0625);
         int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        // (a fixed-point word is compared as an integer first: words clearly below the lowest level -- all the empty ones, and
+        // the thousands of light labels -- never pay the 64-bit int -> double conversion; 2048 covers its rounding)
+        const long long floor3 = (long long)(theta0 * 0.0625 * scale) - 2048;
         auto tally = [&](uint2 a) {
-          const unsigned long long bits = (unsigned long long)__double_as_longlong(word_score(a));  // (empty word: 0, below every level)
+          const long long sfix = (long long)(((unsigned long long)a.y << 32) | a.x);
+          if (sfix < floor3 || sfix == 0) return;
+          const unsigned long long bits = (unsigned long long)__double_as_longlong((double)sfix * inv);
           c0 += bits >= l0; c1 += bits >= l1; c2 += bits >= l2; c3 += bits >= l3;
         };
         for (int i = tid; i < H; i += THREADS) tally(acc[i]);
@@ -385,12 +391,18 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
         tau = DS->lvl[0] >= L ? theta0 : (DS->lvl[1] >= L ? theta0 * 0.75 : (DS->lvl[2] >= L ? theta0 * 0.5 : (DS->lvl[3] >= L ? theta0 * 0.0625 : 0.0)));
       }
       const unsigned long long tb0 = (unsigned long long)__double_as_longlong(tau);
+      const long long floor_tau = (long long)(tau * scale) - 2048;
       for (int i0 = 0; i0 < H; i0 += THREADS) {
         const int i = i0 + tid;
         const uint2 a = i < H ? acc[i] : make_uint2(0u, 0u);
-        const bool nz = (a.x | a.y) != 0u;
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(word_score(a));
-        const bool ok = nz && bits >= tb0;
+        const long long sfix = (long long)(((unsigned long long)a.y << 32) | a.x);
+        const bool nz = sfix != 0;
+        unsigned long long bits = 0ull;
+        bool ok = false;
+        if (nz && sfix >= floor_tau) {
+          bits = (unsigned long long)__double_as_longlong((double)sfix * inv);
+          ok = bits >= tb0;
+        }
         dropped_local |= nz && !ok;
         append(ok, bits, i);
       }
@@ -412,7 +424,7 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
       }
       __syncthreads();
       n = S->ncand;
-      if (n > CMAX) { bail = true; dbg[4]++; }
+      if (n > CMAX) { wide = true; dbg[4]++; }  // (a long run of tied scores at the cut, typically: selected straight from the tables)
       dbg[2] += tau == 0.0;
     }
     const unsigned long long thb = (unsigned long long)__double_as_longlong(tau);  // what the compact arrays were filtered with
@@ -420,11 +432,18 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
 
     // ---- sketch buckets that can hold a kept label: upper bound >= tau (tau > 0 only with >= L candidates above it) ----
     if (!bail) {
+      // smallest bucket value whose upper bound reaches tau (tau = 0: every non-zero bucket)
+      unsigned int sk_floor;
+      {
+        const double qf = tau / sk_inv;  // (division by a power of two: exact)
+        sk_floor = qf >= 4294967295.0 ? 0xffffffffu : (unsigned int)ceil(qf);
+        if (sk_floor == 0u) sk_floor = 1u;
+      }
       int any = 0;
       for (int i0 = 0; i0 < R; i0 += THREADS) {
         const int i = i0 + tid;
         const unsigned int a = i < R ? sk[i] : 0u;
-        const bool al = a != 0u && (double)a * sk_inv >= tau;
+        const bool al = a >= sk_floor;
         dropped_local |= a != 0u && !al;
         const unsigned m = __ballot_sync(FULL, al);
         if (lane == 0 && i < R) s_alive[i >> 5] = m;
@@ -433,6 +452,8 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
       any = __syncthreads_or(any);
       DPROF_MARK(3);
       dbg[1] += any != 0;
+      if (any && clen > 1024) dbg[6]++;   // (profiling: pass 2 on a hub)
+      if (clen > 1024) dbg[3]++;          // (profiling: hubs seen)
       if (any) {
         // (the node's own label is normally a pre label; if it lost its home slot its self term went to the sketch too)
         if (tid == 0 && wanted(self_id) && !tail_add(self_id, xself)) S->spilled = 1;
@@ -457,7 +478,7 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
           }
           __syncthreads();
           n = S->ncand;
-          if (n > CMAX) { bail = true; dbg[4]++; }
+          if (n > CMAX && !wide) { wide = true; dbg[4]++; }
         }
       }
       DPROF_MARK(4);
@@ -466,28 +487,43 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
     int kept = 0, old_cnt = 0;
     if (!bail) {
       // ---- keepTop(L) with the canonical tie-break (pprInternal.h:109-137) ----
-      const unsigned long long* kb = c_bits;
-      const int* ki = c_id;
+      // candidates: the compact arrays, or -- wide -- the tables themselves: dense words [0, H), then the tail table's list
+      const int ntl = S->tcount;
+      const int nidx = wide ? H + ntl : n;
+      auto wbits = [&](int i) -> unsigned long long {
+        const uint2 a = i < H ? acc[i] : t_acc[t_list[i - H]];
+        return (unsigned long long)__double_as_longlong(word_score(a));
+      };
+      auto kbits = [&](int i) -> unsigned long long { return wide ? wbits(i) : c_bits[i]; };
+      auto kid = [&](int i) -> int {
+        if (!wide) return c_id[i];
+        if (i < H) return i;
+        const int tk = t_keys[t_list[i - H]];
+        return tk < 0 ? ~tk : tk;
+      };
+      auto kok = [&](int i) -> bool {
+        if (!wide) return true;
+        const unsigned long long b = wbits(i);
+        return b != 0ull && b >= thb;
+      };
       Threshold thr;
       thr.bits = thb;  // n <= L: everything that reached the bound is kept, nothing below it is
       thr.id_max = 0x7fffffff;
       kept = n;
-      auto all = [](int) { return true; };
       const int dropped_any = __syncthreads_or(dropped_local ? 1 : 0);
       if (n > L) {
         kept = L;
         bool tie;
         int krem;
-        auto keyfn = [&](int i) { return kb[i]; };
         int ntied = 0;
-        if (n * n <= 256 * THREADS) {
-          // few candidates (the filter leaves little more than L): every thread ranks its candidates against all of them --
+        if (!wide && n <= 160) {
+          // few candidates (the bound leaves little more than L): every thread ranks its candidate against all of them --
           // two barriers instead of the radix select's dozen. The value with (above < L <= above + equal) is the cut.
           for (int i = tid; i < n; i += THREADS) {
-            const unsigned long long b = kb[i];
+            const unsigned long long b = c_bits[i];
             int gt = 0, eq = 0;
 #pragma unroll 4
-            for (int j = 0; j < n; j++) { const unsigned long long x = kb[j]; gt += x > b; eq += x == b; }
+            for (int j = 0; j < n; j++) { const unsigned long long x = c_bits[j]; gt += x > b; eq += x == b; }
             if (gt < L && gt + eq >= L) { DS->cut_bits = b; DS->cut_gt = gt; DS->cut_eq = eq; }  // (same values from every writer)
           }
           __syncthreads();
@@ -497,19 +533,19 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
           tie = DS->cut_gt + DS->cut_eq > L;
           __syncthreads();
         } else {
-          thr.bits = block_radix_select(n, L, keyfn, all, S, &tie, &krem, &ntied);
+          thr.bits = block_radix_select(nidx, L, kbits, kok, S, &tie, &krem, &ntied);
         }
         if (tie) {
           const unsigned long long tb = thr.bits;
           if (ntied <= 32) {
-            auto densefn = [&](int i) { return dense_of[ki[i]]; };
-            thr.id_max = block_small_tie_cut(n, krem, tb, keyfn, all, densefn, S);
+            auto densefn = [&](int i) { return dense_of[kid(i)]; };
+            thr.id_max = block_small_tie_cut(nidx, krem, tb, kbits, kok, densefn, S);
           } else {
-            auto idkey = [&](int i) { return (unsigned long long)(0x7fffffff - dense_of[ki[i]]); };
-            auto tied = [&](int i) { return kb[i] == tb; };
+            auto idkey = [&](int i) { return (unsigned long long)(0x7fffffff - dense_of[kid(i)]); };
+            auto tied = [&](int i) { return kok(i) && kbits(i) == tb; };
             bool tie2;
             int krem2;
-            const unsigned long long tid_key = block_radix_select(n, krem, idkey, tied, S, &tie2, &krem2);
+            const unsigned long long tid_key = block_radix_select(nidx, krem, idkey, tied, S, &tie2, &krem2);
             thr.id_max = 0x7fffffff - (int)tid_key;
           }
           s_ties += (tid == 0);
@@ -529,9 +565,10 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
       if (tid == 0) S->out_pos = 0;
       __syncthreads();
       long long dsum = 0;
-      for (int i = tid; i < n; i += THREADS) {
-        const unsigned long long bits = kb[i];
-        const int id = ki[i];
+      for (int i = tid; i < nidx; i += THREADS) {
+        if (!kok(i)) continue;
+        const unsigned long long bits = kbits(i);
+        const int id = kid(i);
         if (selected(bits, id)) {
           const int pos = atomicAdd(&S->out_pos, 1);
           const double v = __longlong_as_double((long long)bits);
@@ -584,8 +621,12 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
     DPROF_MARK(6);
     // ---- leave the tables clean ----
     __syncthreads();
-    for (int i = tid; i < H; i += THREADS) acc[i] = make_uint2(0u, 0u);
-    for (int i = tid; i < R; i += THREADS) sk[i] = 0u;
+    {
+      uint4* z = reinterpret_cast<uint4*>(acc);  // 16-byte stores: dense words, then the sketch
+      for (int i = tid; i < H / 2; i += THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+      uint4* zs = reinterpret_cast<uint4*>(sk);
+      for (int i = tid; i < R / 4; i += THREADS) zs[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     {
       const int nt = S->tcount;
       for (int i = tid; i < nt; i += THREADS) {

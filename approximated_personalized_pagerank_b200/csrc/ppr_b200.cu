@@ -203,6 +203,7 @@ struct pprb200_session {
   int sm_count = 148;
   // storage ranges [colour]: exact-order class (out-degree <= hub_threshold), stored first
   int range_begin[2] = {0, 0}, range_end[2] = {0, 0};
+  int range_split[2] = {0, 0};  // exact-order nodes from here on have out-degree <= SEQ_SMALL_DEG
   // order-free class (out-degree > hub_threshold): work items [colour][0 = mid (128-thread CTAs), 1 = big (512)]
   int item_begin[2][2] = {{0, 0}, {0, 0}}, item_end[2][2] = {{0, 0}, {0, 0}};
   int n_items = 0;
@@ -237,7 +238,7 @@ struct pprb200_session {
   unsigned char* d_buf[2] = {nullptr, nullptr};
   size_t buf_bytes = 0;
   unsigned int* d_queue[4] = {nullptr, nullptr, nullptr, nullptr};
-  unsigned int* d_fb_queue = nullptr;  // [2 * n_items] items merge_dense hands over to merge_par: mid class | big class
+  unsigned int* d_fb_queue = nullptr;  // [n_items] items merge_dense hands over to merge_par
   int* d_ncand = nullptr;
   RunState* d_state = nullptr;
   unsigned long long* d_final_stats = nullptr;
@@ -458,8 +459,11 @@ struct HostPlan {
   double prep_ms = 0;
 };
 
+constexpr int SEQ_SMALL_DEG = 3;  // exact-order nodes up to this out-degree fit 512-slot tables: twice the warps per SM
+
 struct RankPlan {
   int range_begin[2] = {0, 0}, range_end[2] = {0, 0};
+  int range_split[2] = {0, 0};  // [range_split, range_end): out-degree <= SEQ_SMALL_DEG (the class is stored by out-degree descending)
   std::vector<int> seq_list;  // world > 1: this rank's positions of the exact-order class, colour-major
   int item_begin[2][2] = {{0, 0}, {0, 0}}, item_end[2][2] = {{0, 0}, {0, 0}};
   int hub_items[2] = {0, 0};
@@ -566,11 +570,19 @@ static void build_rank_plan(const HostPlan& H, int32_t rank, RankPlan& R) {
     if (world == 1) {
       R.range_begin[c] = H.cls_begin[c][0];
       R.range_end[c] = H.cls_end[c][0];
+      R.range_split[c] = R.range_end[c];
+      for (int p = R.range_begin[c]; p < R.range_end[c]; p++)
+        if (H.row_off[(size_t)p + 1] - H.row_off[p] <= SEQ_SMALL_DEG) { R.range_split[c] = p; break; }
     } else {
       R.range_begin[c] = (int)R.seq_list.size();
+      R.range_split[c] = -1;
       for (int p = H.cls_begin[c][0]; p < H.cls_end[c][0]; p++)
-        if (H.owner_of_pos[(size_t)p] == rank) R.seq_list.push_back(p);
+        if (H.owner_of_pos[(size_t)p] == rank) {
+          if (R.range_split[c] < 0 && H.row_off[(size_t)p + 1] - H.row_off[p] <= SEQ_SMALL_DEG) R.range_split[c] = (int)R.seq_list.size();
+          R.seq_list.push_back(p);
+        }
       R.range_end[c] = (int)R.seq_list.size();
+      if (R.range_split[c] < 0) R.range_split[c] = R.range_end[c];
     }
   }
   for (int c = 0; c < 2; c++)
@@ -618,7 +630,7 @@ static int session_from_plan(const HostPlan& H, const RankPlan& R, uint32_t max_
   s->max_deg = H.max_deg; s->max_deg_seq = H.max_deg_seq; s->max_deg_par = R.max_deg_par;
   for (int c = 0; c < 2; c++) {
     s->colour_count[c] = H.colour_count[c];
-    s->range_begin[c] = R.range_begin[c]; s->range_end[c] = R.range_end[c];
+    s->range_begin[c] = R.range_begin[c]; s->range_end[c] = R.range_end[c]; s->range_split[c] = R.range_split[c];
     s->hub_items[c] = R.hub_items[c];
     for (int k = 0; k < 2; k++) { s->item_begin[c][k] = R.item_begin[c][k]; s->item_end[c][k] = R.item_end[c][k]; }
   }
@@ -671,8 +683,8 @@ static int session_from_plan(const HostPlan& H, const RankPlan& R, uint32_t max_
     s->tbl_count_cls[1] = s->sm_count + 8;      // >= CTAs in flight of the big instantiation
     s->tbl_count_cls[0] = s->sm_count * 3 + 8;  // ... of the mid instantiation
     // merge_dense_kernel in front: merge_par only sees the init pass (multiplicities: small tables), split hubs and the
-    // few hand-overs -- 64 tables are plenty (a CTA that finds none free waits for one), and 68 GB of pool become 28
-    if (dense_enabled()) s->tbl_count_cls[1] = 64;
+    // hand-overs (a CTA that finds no table free waits for one): 68 GB of pool become 46
+    if (dense_enabled()) s->tbl_count_cls[1] = 104;
     s->tbl_first[1] = 0;
     s->tbl_first[0] = s->tbl_count_cls[1];
     s->pool_off[1] = 0;
@@ -683,7 +695,7 @@ static int session_from_plan(const HostPlan& H, const RankPlan& R, uint32_t max_
         (rc = dev_alloc(&s->d_item_len, (size_t)s->n_items)) || (rc = dev_alloc(&s->d_pool, pool_bytes)) ||
         (rc = dev_alloc(&s->d_tbl_inuse, (size_t)n_tables)) || (rc = dev_alloc(&s->d_tbl_count, (size_t)n_tables)) ||
         (rc = dev_alloc(&s->d_node_tbl, (size_t)M)) || (rc = dev_alloc(&s->d_node_done, (size_t)M)) ||
-        (rc = dev_alloc(&s->d_fb_queue, (size_t)2 * s->n_items))) {
+        (rc = dev_alloc(&s->d_fb_queue, (size_t)s->n_items))) {
       session_free(s);
       return rc;
     }
@@ -795,10 +807,12 @@ static cudaError_t launch_stage(pprb200_session* s, const MergeParams& P, int gr
 }
 
 // Enqueue the table-size cascade for one colour (or, MC, for everything): 1024 -> 2048 -> 4096 -> 16384 -> global.
-static int enqueue_cascade(pprb200_session* s, MergeParams P, int range_begin, int range_end, int L) {
+static int enqueue_cascade(pprb200_session* s, MergeParams P, int range_begin, int range_end, int L, int range_split = -1) {
   const int Lp = roundup4(L);
   P.Lp = Lp;
   P.L = L;
+  // the low-degree tail of the range on 512-slot tables (27 warps per SM instead of 14), if those can never overflow there
+  if (range_split < range_begin || range_split > range_end || stage_limit(512, Lp) < SEQ_SMALL_DEG * Lp + 1 || getenv("PPRB200_NO_SMALL_STAGE")) range_split = range_end;
   const int caps[4] = {1024, 2048, 4096, 16384};
   const int warps[4] = {14, 7, 3, 1};
   bool have_source = false;  // false: next stage reads the range; true: reads queue `qsrc`
@@ -810,13 +824,23 @@ static int enqueue_cascade(pprb200_session* s, MergeParams P, int range_begin, i
     MergeParams Q = P;
     Q.limit = limit;
     Q.work_idx = work_idx++;
-    if (!have_source) { Q.range_begin = range_begin; Q.range_end = range_end; Q.queue_in = nullptr; Q.queue_in_idx = -1; }
+    const bool first = !have_source;
+    if (first) { Q.range_begin = range_begin; Q.range_end = range_split; Q.queue_in = nullptr; Q.queue_in_idx = -1; }
     else { Q.queue_in = s->d_queue[qsrc]; Q.queue_in_idx = qsrc; }
     const int qdst = qsrc + 1;
     Q.queue_out = s->d_queue[qdst];
     Q.queue_out_idx = qdst;
     const size_t smem = (size_t)warps[i] * ((size_t)caps[i] * 14 + 1040);
-    cudaError_t e;
+    cudaError_t e = cudaSuccess;
+    if (first && range_split < range_end) {
+      MergeParams T = Q;
+      T.range_begin = range_split; T.range_end = range_end;
+      T.limit = stage_limit(512, Lp);
+      T.work_idx = 5;
+      e = launch_stage<512, 27, unsigned short>(s, T, s->sm_count, (size_t)27 * ((size_t)512 * 14 + 1040), nullptr, 0, 0);
+      if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge stage (512-slot tables) launch failed: %s", cudaGetErrorString(e));
+    }
+    if (first && range_split == range_begin) { have_source = true; qsrc = qdst; continue; }  // (nothing but low-degree nodes)
     if (i == 0) e = launch_stage<1024, 14, unsigned short>(s, Q, s->sm_count, smem, nullptr, 0, 0);
     else if (i == 1) e = launch_stage<2048, 7, unsigned short>(s, Q, s->sm_count, smem, nullptr, 0, 0);
     else if (i == 2) e = launch_stage<4096, 3, unsigned short>(s, Q, s->sm_count, smem, nullptr, 0, 0);
@@ -948,8 +972,8 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
       D.item_base = b + n_hub;
       D.chunk = s->chunk;
       D.work_idx = 8 + cls;
-      D.fb_queue = s->d_fb_queue + (size_t)cls * s->n_items;  // each class hands over to its own merge_par instantiation
-      D.fb_idx = 4 + cls;
+      D.fb_queue = s->d_fb_queue;
+      D.fb_idx = 4;
       D.prof = s->d_prof ? s->d_prof + (size_t)cls * s->sm_count * 8 * 8 : nullptr;
       s->cur = cls == 0 ? side : s->stream;
       cudaError_t err;
@@ -959,15 +983,15 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
       } else {
         static const int cfg = getenv("PPRB200_MID_CFG") ? atoi(getenv("PPRB200_MID_CFG")) : 0;  // A/B hook
         if (cfg == 3) err = launch_dense<2048, 8192, 1024, 512, PAR_MID_MAX, 256, 3>(s, D, 3);
-        else if (cfg == 2) err = launch_dense<4096, 8192, 2048, 1024, PAR_MID_MAX, 512, 2>(s, D, 2);
-        else err = launch_dense<1024, 4096, 512, 512, PAR_MID_MAX, 128, 5>(s, D, 5);
+        else if (cfg == 5) err = launch_dense<1024, 4096, 512, 512, PAR_MID_MAX, 128, 5>(s, D, 5);
+        else err = launch_dense<4096, 8192, 2048, 1024, PAR_MID_MAX, 512, 2>(s, D, 2);  // measured best on R-MAT-22 (profiles/r2/sweeps.txt)
       }
       if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_dense launch failed: %s", cudaGetErrorString(err));
     }
   }
   if (dense && s->item_end[c][1] > s->item_begin[c][0]) {
-    // whatever the dense kernels handed over (first updates of low-degree nodes, a few overflows): merge_par from the queues,
-    // the mid class on its 128-thread instantiation (three CTAs per SM), the big class on the 512-thread one
+    // whatever the dense kernels handed over (first updates of low-degree nodes, a few overflows): merge_par from the queue, on
+    // its 512-thread two-pass instantiation (measured: the 128-thread one is slower on these, profiles/r2/sweeps.txt)
     if (s->overlap) {
       cudaEventRecord(s->ev_join[0], side);
       cudaStreamWaitEvent(s->stream, s->ev_join[0], 0);
@@ -977,17 +1001,13 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
     P.item_len = s->d_item_len;
     P.n_items = 0;
     P.prof = nullptr;
+    P.item_queue = s->d_fb_queue;
+    P.queue_idx = 4;
+    P.work_idx = 10;
+    par_class(1);
     s->cur = s->stream;
-    for (int cls = 1; cls >= 0; cls--) {
-      if (s->item_end[c][cls] == s->item_begin[c][cls]) continue;
-      P.item_queue = s->d_fb_queue + (size_t)cls * s->n_items;
-      P.queue_idx = 4 + cls;
-      P.work_idx = 10 + cls;
-      par_class(cls);
-      cudaError_t err = cls == 1 ? launch_par<8192, 2048, 3072, PAR_CHUNK_MAX, 8192, 512>(s, P, std::min(s->sm_count, s->tbl_count_cls[1]))
-                                 : launch_par<2048, 2048, 2048, PAR_MID_MAX, 0, 128>(s, P, s->sm_count * 3);
-      if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_par (hand-over queue) launch failed: %s", cudaGetErrorString(err));
-    }
+    cudaError_t err = launch_par<8192, 2048, 3072, PAR_CHUNK_MAX, 8192, 512>(s, P, std::min(s->sm_count, s->tbl_count_cls[1]));
+    if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_par (hand-over queue) launch failed: %s", cudaGetErrorString(err));
   }
   s->cur = s->stream;
   return PPRB200_OK;
@@ -1004,7 +1024,7 @@ static int enqueue_colour(pprb200_session* s, const MergeParams& Q, int c, int L
   }
   if ((rc = enqueue_par(s, Q, c, L))) return rc;
   s->cur = s->overlap ? s->aux[1] : s->stream;
-  if (s->range_end[c] > s->range_begin[c] && (rc = enqueue_cascade(s, Q, s->range_begin[c], s->range_end[c], L))) return rc;
+  if (s->range_end[c] > s->range_begin[c] && (rc = enqueue_cascade(s, Q, s->range_begin[c], s->range_end[c], L, s->range_split[c]))) return rc;
   s->cur = s->stream;
   if (s->overlap) {
     for (int i = 0; i < 2; i++) {

@@ -21,7 +21,7 @@ for rep in range(2):
     if dense:
         d = (C.c_ulonglong * 8)()
         lib.pprb200_debug_counters(s.handle, d)
-        print("  dense kernels: nodes done %d, ran pass 2 %d, tau=0 %d; handed over: untrusted %d, candidates>CMAX %d, tail full %d, split-hub items %d, old basket not full %d" % tuple(d[i] for i in range(8)))
+        print("  dense kernels: nodes done %d, ran pass 2 %d, tau=0 %d; hubs (>1024 successors) seen %d / ran pass 2 %d; handed over: candidates>CMAX %d, tail full %d, old basket not full %d" % (d[0], d[1], d[2], d[3], d[6], d[4], d[5], d[7]))
     buf = np.zeros(2 * 148 * 8 * 8, dtype=np.uint64); n = C.c_int(0)
     lib.pprb200_debug_prof(s.handle, buf.ctypes.data_as(C.c_void_p), C.byref(n))
     buf = buf.reshape(2, 148 * 8, 8)
