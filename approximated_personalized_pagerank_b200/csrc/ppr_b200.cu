@@ -369,9 +369,11 @@ static int default_mid_deg(int32_t n) {
 // becomes the tail of every iteration (R-MAT-22 on 8 GPUs: 99 M node-iterations/s with 4096, 92 M with 32768).
 static int default_chunk(int32_t n, int world) {
   if (const char* e = getenv("PPRB200_CHUNK")) return std::min(1 << 20, std::max(32, atoi(e)));
-  // one GPU, merge_dense_kernel: a whole hub on one CTA (the largest R-MAT-22 hub, 16 M entries, is ~8 ms of a >= 10 ms
+  // merge_dense_kernel: a whole hub on one CTA (the largest R-MAT-22 hub, 16 M entries, is ~8 ms of a >= 10 ms
   // iteration) beats its chunks meeting in an L2-resident table by a wide margin (profiles/r2/launches_r22_v2.txt)
-  if (world <= 1 && dense_enabled()) return 1 << 20;
+  // (several GPUs: the same. Measured on 2 B200s, R-MAT-22: the 23 hubs above 32768 successors, split into chunks for
+  // balance, cost ~10 ms per iteration and rank on merge_par -- a fifth of the iteration -- and 1.29x was all two GPUs gave)
+  if (dense_enabled()) return 1 << 20;
   int c = 2048;
   while (c < 32768 && (long long)c * 64 * std::max(world, 1) < (long long)n) c <<= 1;
   return c;
@@ -1351,6 +1353,28 @@ static int session_fetch_impl(pprb200_session* s, int32_t* out_ids, double* out_
   return PPRB200_OK;
 }
 
+// CUDA loads a kernel's code onto a device at its first launch there, and that load can wait for the device to go idle. In a
+// one-process multi-GPU run the first kernels of rank 0 spin in the mailbox barrier until rank 1 -- enqueued by the same host
+// thread, later -- arrives: a first-use load behind such a kernel would never return. So every kernel this library can launch
+// is loaded on the current device up front (cudaFuncGetAttributes does that), before anything that waits for a peer is enqueued.
+template <typename F>
+static void preload(F* kernel) {
+  cudaFuncAttributes attr;
+  cudaFuncGetAttributes(&attr, reinterpret_cast<const void*>(kernel));
+}
+static void preload_kernels() {
+  preload(state_reset_kernel); preload(pool_init_kernel); preload(phase_end_kernel); preload(iter_end_kernel); preload(final_topk_kernel);
+  preload(merge_seq_kernel<512, 27, unsigned short>); preload(merge_seq_kernel<1024, 14, unsigned short>);
+  preload(merge_seq_kernel<2048, 7, unsigned short>); preload(merge_seq_kernel<4096, 3, unsigned short>);
+  preload(merge_seq_kernel<16384, 1, unsigned short>); preload(merge_seq_kernel<0, 4, unsigned int>);
+  preload(merge_par_kernel<8192, 2048, 3072, PAR_CHUNK_MAX, 8192, 512>); preload(merge_par_kernel<2048, 2048, 2048, PAR_MID_MAX, 0, 128>);
+  preload(merge_dense_kernel<8192, 16384, 4096, 2048, 1024, 512, 1>); preload(merge_dense_kernel<8192, 16384, 4096, 2048, 1024, 1024, 1>);
+  preload(merge_dense_kernel<2048, 8192, 1024, 512, PAR_MID_MAX, 256, 3>); preload(merge_dense_kernel<1024, 4096, 512, 512, PAR_MID_MAX, 128, 5>);
+  preload(merge_dense_kernel<4096, 8192, 2048, 1024, PAR_MID_MAX, 512, 2>);
+  preload(mc_walk_kernel<false, 128>); preload(mc_walk_kernel<false, 256>); preload(mc_walk_kernel<true, 128>); preload(mc_walk_kernel<true, 256>);
+  cudaGetLastError();
+}
+
 static std::mutex g_api_mutex;  // one run at a time per process (SURVEY.md 8b re-entrancy)
 
 template <int BT>
@@ -1565,6 +1589,7 @@ int pprb200_session_attach_local(pprb200_session** all, int32_t world) {
     pd.timeout_cycles = peer_timeout_cycles();
     for (int q = 0; q < world; q++) { pd.buf[q][0] = all[q]->d_buf[0]; pd.buf[q][1] = all[q]->d_buf[1]; pd.mbox[q] = all[q]->d_mbox; }
     cudaSetDevice(all[r]->device);
+    preload_kernels();                      // (see preload_kernels: no first-use code load behind a kernel that waits for a peer)
     cudaStreamSynchronize(all[r]->stream);  // mailbox zeroed before anybody posts
     all[r]->peers = pd;
     all[r]->attached = true;
@@ -1826,7 +1851,11 @@ static int run_oneshot(const int64_t* row_ptr, const int32_t* col, int32_t n, co
       ss[(size_t)r]->peers = pd;
       ss[(size_t)r]->attached = true;
     }
-    for (int r = 0; r < world; r++) { cudaSetDevice(devs[(size_t)r]); cudaStreamSynchronize(ss[(size_t)r]->stream); }  // mailboxes zeroed everywhere before anybody posts
+    for (int r = 0; r < world; r++) {
+      cudaSetDevice(devs[(size_t)r]);
+      preload_kernels();
+      cudaStreamSynchronize(ss[(size_t)r]->stream);  // mailboxes zeroed everywhere before anybody posts
+    }
   }
   for (int r = 0; r < world && !rc; r++) {
     cudaSetDevice(devs[(size_t)r]);

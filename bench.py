@@ -366,6 +366,8 @@ def run_job(w, wname, args, cx, steps, warm, hub_threshold, want_e2e=True, want_
         torch.cuda.empty_cache()
         lib.pprb200_release_cached_memory()
         barrier()
+        # (the idle ranks wait on the HOST: an NCCL barrier is a kernel spinning on their GPUs, which rank 0 is about to use)
+        dist.barrier(group=cx.cpu_group)
         if rank == 0:
             os.environ["PPR_NUM_GPUS"] = str(world)
             rp, cl = pin(g.row_ptr), pin(g.col)
@@ -392,6 +394,7 @@ def run_job(w, wname, args, cx, steps, warm, hub_threshold, want_e2e=True, want_
                    "d2h_bytes_per_step": int(n * K * 12 + n * 4), "ms_per_step": 1e3 * sec / e_steps, "n_gpus_used": int(st.n_gpus),
                    "host_prep_ms": st.prep_ms, "kernel_ms": st.kernel_ms, "d2h_ms": st.d2h_ms,
                    "api": f"pprb200_grank / pprb200_mccompletepathv2 with PPR_NUM_GPUS={world}: one process, one host plan, a session per device over peer access"}
+        dist.barrier(group=cx.cpu_group)
         barrier()
 
     if world > 1:
@@ -495,8 +498,10 @@ def main():
     if args.gpus != cx.world and cx.world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={cx.world}")
     torch.cuda.set_device(cx.local_rank)
+    cx.cpu_group = None
     if cx.world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", cx.local_rank))
+        cx.cpu_group = dist.new_group(backend="gloo")  # host-side waits (no kernel on the GPU)
     cx.lib = _lib.load()
     if cx.lib.pprb200_device_count() < 1:
         raise SystemExit("bench.py needs an sm_100 GPU (no CPU fallback)")
