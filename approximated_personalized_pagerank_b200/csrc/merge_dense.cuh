@@ -28,6 +28,44 @@
 
 namespace pprb200 {
 
+// HUB TEAMS. A hub with tens of thousands of successors is the critical path of its iteration when one CTA owns it (the
+// largest R-MAT-22 hub: 16 M entries, two passes, ~15 ms -- more than the whole iteration takes on 8 GPUs). Its successor
+// list is cut into chunks that consecutive work items hand to different CTAs (a team). Every member runs pass 1 on its
+// chunk into its own shared-memory tables and adds what it found into the team's staging area in global memory (L2): the
+// tables are position-compatible -- dense words by label, sketch buckets by hash, pre words by home slot (pre labels are
+// placed deterministically for teams) -- so the staging area is simply their sum. The member that flushes last loads the
+// totals and carries on exactly as the single owner would; if pass 2 is needed it publishes the alive bitmap, every member
+// runs pass 2 on its chunk and appends its exact (label, sum) pairs to the staging area, and the last member merges them.
+// Members wait for each other in flight (spinning on the team header), which cannot deadlock: work items are handed out in
+// order, a team's chunks are consecutive, and a team has at most TEAM_MAX_CHUNKS (< CTAs in the grid) of them.
+constexpr int TEAM_MAX_CHUNKS = 48;
+
+struct TeamInfo {
+  int regular_item;  // global index of the hub's undivided work item (what is handed to merge_par_kernel if the team gives up)
+  int nchunks;
+};
+
+struct TeamHeader {
+  unsigned int done1;       // members that flushed pass 1
+  unsigned int done2;       // members that appended their pass-2 sums
+  unsigned int decision;    // 0 pending, 1 no pass 2, 2 pass 2 (alive bitmap published), 3 team gives up
+  unsigned int tail_count;  // (label, sum) pairs appended by pass 2
+  unsigned int bad;         // bit 0: an untrusted contribution / wrapped bucket, bit 1: a member's tail table overflowed
+  unsigned int edges;       // successors read by the members (statistics)
+  unsigned long long merged;  // basket entries merged by the members (statistics)
+};
+
+struct TeamTailEntry {
+  int key;
+  int pad;
+  unsigned long long acc;
+};
+
+template <int H, int R, int TCAP, int THREADS>
+constexpr size_t team_stage_bytes() {
+  return (size_t)H * 8 + (size_t)TCAP * 8 + (size_t)R * 4 + (size_t)R / 8 + (size_t)TEAM_MAX_CHUNKS * (size_t)(TCAP * 13 / 16 - THREADS) * sizeof(TeamTailEntry);
+}
+
 struct DenseParams {
   MergeParams M;
   const int* item_pos;          // work items of this launch: node position,
@@ -40,6 +78,16 @@ struct DenseParams {
   unsigned int* fb_queue;       // items handed to merge_par_kernel
   int fb_idx;                   // its length: st->qcount[fb_idx]
   unsigned long long* prof;     // optional [gridDim.x * 8] phase cycle counters (PPRB200_PROF=1)
+  // hub teams (below): work indices [0, n_team_items) are chunks of team hubs, the rest the items above
+  const int* team_item_pos;
+  const long long* team_item_begin;
+  const int* team_item_len;
+  const int* team_item_team;
+  int n_team_items;
+  const TeamInfo* teams;
+  TeamHeader* team_hdr;
+  unsigned char* stage;         // team t's staging area: stage + t * stage_bytes
+  size_t stage_bytes;
 };
 
 struct DenseShared {
@@ -47,6 +95,11 @@ struct DenseShared {
   int ncol;      // non-sink column words staged for the current tile
   int bail;      // hand the node to the general kernel
   int lvl[4];    // exact candidates >= theta0, 3/4 theta0, 1/2 theta0, 1/16 theta0
+  int team_last;      // this CTA flushed last: it finishes the team's hub
+  int team_decision;  // what the waiting members read from the team header
+  unsigned int team_base;  // where this member's pass-2 pairs go in the staging area
+  unsigned int team_edges;          // the whole team's statistics (finishing member)
+  unsigned long long team_merged;
   unsigned long long cut_bits;  // rank-count select: the L-th largest score,
   int cut_gt, cut_eq;           //   candidates above it / equal to it
 };
@@ -56,7 +109,9 @@ constexpr size_t dense_smem_bytes() {
   return (size_t)H * 8 + (size_t)R * 4 + (size_t)CMAX * 12 + (size_t)TCAP * 14 + (size_t)COLCAP * 4 + (size_t)R / 8 + sizeof(DenseShared) + 16;
 }
 
-template <int H, int R, int TCAP, int CMAX, int COLCAP, int THREADS, int MINB>
+// TEAMS: the instantiation that serves hub teams' chunk items (launched with those alone); without it the team code is
+// compiled out -- it costs the 64-register instantiations ~6 % in spills (profiles/r2/sweeps.txt)
+template <int H, int R, int TCAP, int CMAX, int COLCAP, int THREADS, int MINB, bool TEAMS = false>
 __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams P) {
   constexpr int NW = THREADS / 32;
   constexpr int TLIMIT = TCAP * 13 / 16 - THREADS;  // distinct tail labels admitted (concurrent inserts overshoot by < THREADS)
@@ -175,14 +230,27 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
     if (tid == 0) { S->item = atomicAdd(&st->work[P.work_idx], 1u); DS->bail = 0; S->ncand = 0; DS->lvl[0] = DS->lvl[1] = DS->lvl[2] = DS->lvl[3] = 0; }
     __syncthreads();
     const unsigned int item = S->item;
-    if (item >= (unsigned)P.n_items) break;
+    if (item >= (unsigned)(P.n_team_items + P.n_items)) break;
     DPROF_MARK(0);
-    const int p = P.item_pos[item];
-    const long long cb = P.item_begin[item];
-    const int clen = P.item_len[item];
+    const int team = (TEAMS && item < (unsigned)P.n_team_items) ? P.team_item_team[item] : -1;
+    const unsigned int ritem = item - (unsigned)P.n_team_items;  // index into the undivided items (team < 0)
+    const int p = team >= 0 ? P.team_item_pos[item] : P.item_pos[ritem];
+    const long long cb = team >= 0 ? P.team_item_begin[item] : P.item_begin[ritem];
+    const int clen = team >= 0 ? P.team_item_len[item] : P.item_len[ritem];
     const long long deg = M.g.row_off[p + 1] - M.g.row_off[p];
-    if (deg > (long long)P.chunk) {  // a chunk of a split hub: the general kernel's job
-      if (tid == 0) { P.fb_queue[atomicAdd(&st->qcount[P.fb_idx], 1u)] = (unsigned int)P.item_base + item; dbg[6]++; }
+    const bool first_chunk = cb == M.g.row_off[p];
+    const int team_n = team >= 0 ? P.teams[team].nchunks : 1;
+    TeamHeader* const hdr = team >= 0 ? P.team_hdr + team : nullptr;
+    unsigned char* const stg = team >= 0 ? P.stage + (size_t)team * P.stage_bytes : nullptr;
+    unsigned long long* const g_dense = reinterpret_cast<unsigned long long*>(stg);
+    unsigned long long* const g_pre = g_dense + H;
+    unsigned int* const g_sk = reinterpret_cast<unsigned int*>(g_pre + TCAP);
+    unsigned int* const g_alive = g_sk + R;
+    TeamTailEntry* const g_tail = reinterpret_cast<TeamTailEntry*>(g_alive + R / 32);
+    // the work item handed to merge_par_kernel when this node cannot be finished here (a team: its undivided item)
+    const unsigned int handover_item = team >= 0 ? (unsigned int)P.teams[team].regular_item : (unsigned int)P.item_base + ritem;
+    if (team < 0 && deg > (long long)P.chunk) {  // a chunk of a hub split for merge_par_kernel: the general kernel's job
+      if (tid == 0) { P.fb_queue[atomicAdd(&st->qcount[P.fb_idx], 1u)] = handover_item; dbg[6]++; }
       continue;
     }
     const int self_id = M.g.label[p];
@@ -202,12 +270,27 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
       const double* osc = reinterpret_cast<const double*>(old + (size_t)Lp * 4);
       unsigned long long mn = ~0ull;
       long long cntv = 0;
+      int* const owner = reinterpret_cast<int*>(c_bits);  // (teams) home slot -> smallest old-basket index that wants it
+      if (team >= 0) {
+        static_assert((size_t)CMAX * 8 >= (size_t)TCAP * 4, "the candidate array doubles as the owner array");
+        for (int i = tid; i < TCAP; i += THREADS) owner[i] = 0x7fffffff;
+        __syncthreads();
+        for (int i = tid; i < Lp + 1; i += THREADS) {
+          const int k = i < Lp ? oid[i] : self_id;
+          if (k >= H) atomicMin(&owner[home_of(hash_key(k))], i);
+        }
+        __syncthreads();
+      }
       for (int i = tid; i < Lp + 1; i += THREADS) {
         const int k = i < Lp ? oid[i] : self_id;
         if (i < Lp && k >= 0) { const unsigned long long b = (unsigned long long)__double_as_longlong(osc[score_index(i, Lp)]); mn = b < mn ? b : mn; cntv++; }
         if (k >= H) {
           const unsigned int hm = home_of(hash_key(k));
-          if (atomicCAS(&t_keys[hm], KEY_EMPTY, ~k) == KEY_EMPTY) t_list[atomicAdd(&S->tcount, 1)] = (unsigned short)hm;
+          if (team >= 0) {  // every member of a team must place the same labels in the same slots: lowest index wins
+            if (owner[hm] == i) { t_keys[hm] = ~k; t_list[atomicAdd(&S->tcount, 1)] = (unsigned short)hm; }
+          } else if (atomicCAS(&t_keys[hm], KEY_EMPTY, ~k) == KEY_EMPTY) {
+            t_list[atomicAdd(&S->tcount, 1)] = (unsigned short)hm;
+          }
         }
       }
       block_reduce_min_sum(mn, cntv, S->red_a);
@@ -219,11 +302,14 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
       // a candidate -- the general kernel's job; hand the node over before reading a single successor basket
       __syncthreads();
       for (int i = tid; i < npre; i += THREADS) { const int s2 = t_list[i]; t_keys[s2] = KEY_EMPTY; }
-      if (tid == 0) { P.fb_queue[atomicAdd(&st->qcount[P.fb_idx], 1u)] = (unsigned int)P.item_base + item; s_requeue++; dbg[7]++; S->tcount = 0; }
+      if (tid == 0) {
+        if (first_chunk) { P.fb_queue[atomicAdd(&st->qcount[P.fb_idx], 1u)] = handover_item; s_requeue++; dbg[7]++; }  // (a team: once)
+        S->tcount = 0;
+      }
       continue;
     }
     bool bad = false;            // this thread saw a contribution that must not be trusted
-    if (tid == 0) {              // the self term (grank.h:101 / mccompletepathv2.h:226)
+    if (tid == 0 && first_chunk) {  // the self term (grank.h:101 / mccompletepathv2.h:226)
       bad |= contribute(self_id, xself);
     }
 
@@ -355,8 +441,118 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
     sweep(1);
     DPROF_MARK(1);
     bool bail = __syncthreads_or(bad ? 1 : 0) != 0;  // (also: pass 1 complete)
-    (void)bail;
+    bool team_member = false;  // a team member that did not flush last: it only serves pass 2
+    if (team >= 0) {
+      // add this chunk's sums into the team's staging area; whoever arrives last takes the totals
+      bool wrapped = false;
+      for (int i = tid; i < H; i += THREADS) {
+        const uint2 a = acc[i];
+        if ((a.x | a.y) != 0u) atomicAdd(&g_dense[i], ((unsigned long long)a.y << 32) | a.x);
+      }
+      for (int i = tid; i < npre; i += THREADS) {
+        const int sl = t_list[i];
+        const uint2 a = t_acc[sl];
+        if ((a.x | a.y) != 0u) atomicAdd(&g_pre[sl], ((unsigned long long)a.y << 32) | a.x);
+      }
+      for (int i = tid; i < R; i += THREADS) {
+        const unsigned int v = sk[i];
+        if (v) { const unsigned int o = atomicAdd(&g_sk[i], v); wrapped |= o + v < o; }
+      }
+      if (__syncthreads_or(wrapped ? 1 : 0)) bail = true;
+      const unsigned long long mg_chunk = (unsigned long long)block_reduce_sum_ll((long long)merged, S->red_a);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        if (bail) atomicOr(&hdr->bad, 1u);
+        atomicAdd(&hdr->merged, mg_chunk);
+        atomicAdd(&hdr->edges, (unsigned int)clen);
+        __threadfence();
+        DS->team_last = atomicAdd(&hdr->done1, 1u) == (unsigned)team_n - 1u;
+        if (DS->team_last) {
+          __threadfence();
+          DS->team_merged = *reinterpret_cast<volatile unsigned long long*>(&hdr->merged);
+          DS->team_edges = *reinterpret_cast<volatile unsigned int*>(&hdr->edges);
+        }
+      }
+      __syncthreads();
+      if (DS->team_last) {
+        __threadfence();
+        for (int i = tid; i < H; i += THREADS) {
+          const unsigned long long v = __ldcg(&g_dense[i]);
+          acc[i] = make_uint2((unsigned int)v, (unsigned int)(v >> 32));
+          if (v) g_dense[i] = 0ull;  // (the staging area is left clean for the next iteration)
+        }
+        for (int i = tid; i < npre; i += THREADS) {
+          const int sl = t_list[i];
+          const unsigned long long v = __ldcg(&g_pre[sl]);
+          t_acc[sl] = make_uint2((unsigned int)v, (unsigned int)(v >> 32));
+          if (v) g_pre[sl] = 0ull;
+        }
+        for (int i = tid; i < R; i += THREADS) {
+          const unsigned int v = __ldcg(&g_sk[i]);
+          sk[i] = v;
+          if (v) g_sk[i] = 0u;
+        }
+        if (*reinterpret_cast<volatile unsigned int*>(&hdr->bad) & 1u) bail = true;
+      } else {
+        team_member = true;
+        uint4* z = reinterpret_cast<uint4*>(acc);
+        for (int i = tid; i < H / 2; i += THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        uint4* zs = reinterpret_cast<uint4*>(sk);
+        for (int i = tid; i < R / 4; i += THREADS) zs[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < npre; i += THREADS) t_acc[t_list[i]] = make_uint2(0u, 0u);  // (the pre KEYS stay: pass 2 skips those labels)
+      }
+      __syncthreads();
+    }
+    if (team_member) {
+      // wait for the finishing member's verdict; serve pass 2 if it asks for it
+      if (tid == 0) {
+        unsigned int d;
+        while ((d = *reinterpret_cast<volatile unsigned int*>(&hdr->decision)) == 0u) __nanosleep(100);
+        DS->team_decision = (int)d;
+      }
+      __syncthreads();
+      if (DS->team_decision == 2) {
+        __threadfence();
+        for (int i = tid; i < R / 32; i += THREADS) s_alive[i] = __ldcg(&g_alive[i]);
+        __syncthreads();
+        sweep(2);
+        __syncthreads();
+        const int nt1 = S->tcount;
+        if (tid == 0) {
+          DS->team_base = atomicAdd(&hdr->tail_count, (unsigned int)(nt1 - npre));
+          if (S->spilled) atomicOr(&hdr->bad, 2u);
+        }
+        __syncthreads();
+        for (int i = npre + tid; i < nt1; i += THREADS) {
+          const int sl = t_list[i];
+          TeamTailEntry e;
+          e.key = t_keys[sl];
+          e.pad = 0;
+          e.acc = ((unsigned long long)t_acc[sl].y << 32) | t_acc[sl].x;
+          g_tail[DS->team_base + (unsigned int)(i - npre)] = e;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(&hdr->done2, 1u);
+      }
+      // leave the tables clean; this chunk's share of the statistics
+      __syncthreads();
+      {
+        const int ntl = S->tcount;
+        for (int i = tid; i < ntl; i += THREADS) {
+          const int sl = t_list[i];
+          t_keys[sl] = KEY_EMPTY;
+          t_acc[sl] = make_uint2(0u, 0u);
+        }
+      }
+      if (tid == 0) { S->tcount = 0; S->spilled = 0; }  // (this chunk's statistics went into the team header: the finishing member books them)
+      continue;
+    }
 
+    if (team >= 0 && bail) {  // (finishing member) an untrusted contribution somewhere in the team: everybody stops here
+      if (tid == 0) { __threadfence(); *reinterpret_cast<volatile unsigned int*>(&hdr->decision) = 3u; }
+    }
     // ---- exact candidates (dense + pre labels) -> compact (score bits, label) arrays ----
     // scan 1 counts how many reach theta0, 3/4, 1/2, 1/16 of it: tau = the highest level that L of them reach is a lower
     // bound of the cut (0 when none is); scan 2 compacts the candidates >= tau.
@@ -454,11 +650,34 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
       dbg[1] += any != 0;
       if (any && clen > 1024) dbg[6]++;   // (profiling: pass 2 on a hub)
       if (clen > 1024) dbg[3]++;          // (profiling: hubs seen)
+      if (team >= 0) {  // (finishing member) tell the team: done, or pass 2 with this alive bitmap
+        if (any) {
+          for (int i = tid; i < R / 32; i += THREADS) g_alive[i] = s_alive[i];
+          __threadfence();
+        }
+        __syncthreads();
+        if (tid == 0) { __threadfence(); *reinterpret_cast<volatile unsigned int*>(&hdr->decision) = any ? 2u : 1u; }
+      }
       if (any) {
         // (the node's own label is normally a pre label; if it lost its home slot its self term went to the sketch too)
         if (tid == 0 && wanted(self_id) && !tail_add(self_id, xself)) S->spilled = 1;
         sweep(2);
         __syncthreads();
+        if (team >= 0) {
+          // the other members' exact (label, sum) pairs: wait for all of them, then fold them into this table
+          if (tid == 0) {
+            while (*reinterpret_cast<volatile unsigned int*>(&hdr->done2) < (unsigned)team_n - 1u) __nanosleep(100);
+            __threadfence();
+            DS->team_base = *reinterpret_cast<volatile unsigned int*>(&hdr->tail_count);
+            if (*reinterpret_cast<volatile unsigned int*>(&hdr->bad) & 2u) S->spilled = 1;
+          }
+          __syncthreads();
+          const unsigned int npairs = DS->team_base;
+          for (unsigned int i = tid; i < npairs; i += THREADS) {
+            if (!tail_add(__ldcg(&g_tail[i].key), __ldcg(&g_tail[i].acc))) S->spilled = 1;
+          }
+          __syncthreads();
+        }
         if (S->spilled) { bail = true; dbg[5]++; }
         if (!bail) {
           const int nt0 = S->tcount;
@@ -637,16 +856,18 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
     }
     if (bail) {
       // partial sums dropped; merge_par_kernel runs the node from scratch (same sums, global table)
-      if (tid == 0) { P.fb_queue[atomicAdd(&st->qcount[P.fb_idx], 1u)] = (unsigned int)P.item_base + item; s_requeue++; }
+      if (tid == 0) { P.fb_queue[atomicAdd(&st->qcount[P.fb_idx], 1u)] = handover_item; s_requeue++; }
     } else {
-      const unsigned long long mg = (unsigned long long)block_reduce_sum_ll((long long)merged, S->red_a);
+      unsigned long long mg = (unsigned long long)block_reduce_sum_ll((long long)merged, S->red_a);
       if (tid == 0) {
+        unsigned long long ne = (unsigned long long)clen;
+        if (team >= 0) { mg = DS->team_merged; ne = DS->team_edges; }  // the whole team's work
         M.ncand[p] = 0;
         s_merged += mg;
-        s_edges += (unsigned long long)clen;
+        s_edges += ne;
         s_cands += (unsigned long long)n;
         s_nodes += 1;
-        s_bytes += 12ull * mg + 4ull * (unsigned long long)clen + 12ull * (unsigned long long)old_cnt + 12ull * (unsigned long long)kept + 4ull + 16ull;
+        s_bytes += 12ull * mg + 4ull * ne + 12ull * (unsigned long long)old_cnt + 12ull * (unsigned long long)kept + 4ull + 16ull;
       }
     }
     __syncthreads();

@@ -210,7 +210,8 @@ struct pprb200_session {
   int chunk = 4096, mid_deg = 64;
   int hub_items[2] = {0, 0};          // leading items of the big list that are chunks of split hubs (out-degree > chunk)
   bool use_dense = true;              // merge_dense_kernel for single-item nodes (PPRB200_DENSE=0: merge_par only)
-  int dense_threads = 1024;           // CTA size of the big instantiation (PPRB200_DENSE_THREADS)
+  int dense_threads = 512;            // CTA size of the big instantiation (PPRB200_DENSE_THREADS): 512 threads at 128 registers
+                                      // beat 1024 at 64 with spills by 5 % on R-MAT-22 (profiles/r2/sweeps.txt)
   int* d_item_pos = nullptr;
   long long* d_item_off = nullptr;
   int* d_item_len = nullptr;
@@ -239,6 +240,16 @@ struct pprb200_session {
   size_t buf_bytes = 0;
   unsigned int* d_queue[4] = {nullptr, nullptr, nullptr, nullptr};
   unsigned int* d_fb_queue = nullptr;  // [n_items] items merge_dense hands over to merge_par
+  // hub teams
+  int n_team_nodes[2] = {0, 0}, team_first[2] = {0, 0}, team_count[2] = {0, 0}, team_item_begin[2] = {0, 0}, team_item_end[2] = {0, 0};
+  int* d_team_item_pos = nullptr;
+  long long* d_team_item_off = nullptr;
+  int* d_team_item_len = nullptr;
+  int* d_team_item_team = nullptr;
+  TeamInfo* d_teams = nullptr;
+  TeamHeader* d_team_hdr = nullptr;
+  unsigned char* d_stage = nullptr;
+  size_t stage_bytes = 0;
   int* d_ncand = nullptr;
   RunState* d_state = nullptr;
   unsigned long long* d_final_stats = nullptr;
@@ -336,7 +347,8 @@ static void session_free(pprb200_session* s) {
   void* plain[] = {s->d_rowdeg, s->d_seq_list, s->d_row_off, s->d_col, s->d_label, s->d_pos_of, s->d_dense_of, s->d_colour, s->d_queue[0], s->d_queue[1],
                    s->d_queue[2], s->d_queue[3], s->d_ncand, s->d_state, s->d_final_stats, s->d_ws, s->d_out_ids, s->d_out_scores,
                    s->d_out_cnt, s->d_item_pos, s->d_item_off, s->d_item_len, s->d_pool, s->d_walk_ws, s->d_prof, s->d_tbl_inuse,
-                   s->d_tbl_count, s->d_node_tbl, s->d_node_done, s->d_fb_queue};
+                   s->d_tbl_count, s->d_node_tbl, s->d_node_done, s->d_fb_queue, s->d_team_item_pos, s->d_team_item_off,
+                   s->d_team_item_len, s->d_team_item_team, s->d_teams, s->d_team_hdr, s->d_stage};
   for (void* q : plain) dev_free(q);
   for (int i = 0; i < 2; i++) if (s->ev_walk[i]) cudaEventDestroy(s->ev_walk[i]);
   for (int i = 0; i < 2; i++) { if (s->aux[i]) cudaStreamDestroy(s->aux[i]); if (s->ev_join[i]) cudaEventDestroy(s->ev_join[i]); }
@@ -473,7 +485,24 @@ struct RankPlan {
   std::vector<int> item_pos;
   std::vector<long long> item_off;
   std::vector<int> item_len;
+  // hub teams (merge_dense.cuh): the leading n_team_nodes[c] big items of colour c are also cut into chunks
+  int n_team_nodes[2] = {0, 0};
+  int team_first[2] = {0, 0}, team_count[2] = {0, 0};          // into `teams`
+  int team_item_begin[2] = {0, 0}, team_item_end[2] = {0, 0};  // into the team item arrays
+  std::vector<TeamInfo> teams;
+  std::vector<int> team_item_pos, team_item_len, team_item_team;
+  std::vector<long long> team_item_off;
 };
+
+// out-degree above which a big-class node is worked on by a team of CTAs, and the successors per member
+static int team_min_deg() {
+  if (const char* e = getenv("PPRB200_TEAM_DEG")) return std::max(PAR_MID_MAX + 1, atoi(e));
+  return 16384;
+}
+static int team_chunk_len() {
+  if (const char* e = getenv("PPRB200_TEAM_CHUNK")) return std::max(32, atoi(e));
+  return 8192;
+}
 
 static int build_host_plan(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour_in, uint32_t hub_threshold,
                            int32_t world, bool need_colour, HostPlan& H) {
@@ -587,13 +616,36 @@ static void build_rank_plan(const HostPlan& H, int32_t rank, RankPlan& R) {
       if (R.range_split[c] < 0) R.range_split[c] = R.range_end[c];
     }
   }
-  for (int c = 0; c < 2; c++)
+  const bool teams_on = dense_enabled() && !getenv("PPRB200_NO_TEAMS");
+  const long long tdeg = team_min_deg(), tchunk = team_chunk_len();
+  for (int c = 0; c < 2; c++) {
+    R.team_first[c] = (int)R.teams.size();
+    R.team_item_begin[c] = (int)R.team_item_pos.size();
     for (int cls = 1; cls < 3; cls++) {
       R.item_begin[c][cls - 1] = (int)R.item_pos.size();
       for (int p = H.cls_begin[c][cls]; p < H.cls_end[c][cls]; p++) {
         if (H.owner_of_pos[(size_t)p] != rank) continue;  // multi-GPU: somebody else's node
         const long long d = H.row_off[(size_t)p + 1] - H.row_off[p];
         if (d > R.max_deg_par) R.max_deg_par = (int32_t)std::min<long long>(d, INT32_MAX);
+        if (teams_on && cls == 2 && d > tdeg && d <= H.chunk && R.n_team_nodes[c] == (int)R.item_pos.size() - R.item_begin[c][1]) {
+          // (the class is stored by out-degree descending: team hubs are its leading items)
+          const int nch = (int)std::min<long long>(TEAM_MAX_CHUNKS, (d + tchunk - 1) / tchunk);
+          if (nch >= 2) {
+            const long long per = (d + nch - 1) / nch;
+            TeamInfo ti;
+            ti.regular_item = (int)R.item_pos.size();
+            ti.nchunks = 0;
+            for (long long o = 0; o < d; o += per) {
+              R.team_item_pos.push_back(p);
+              R.team_item_off.push_back(H.row_off[p] + o);
+              R.team_item_len.push_back((int)std::min<long long>(per, d - o));
+              R.team_item_team.push_back((int)R.teams.size());
+              ti.nchunks++;
+            }
+            R.teams.push_back(ti);
+            R.n_team_nodes[c]++;
+          }
+        }
         if (cls == 2 && d > H.chunk) R.hub_items[c] += (int)((d + H.chunk - 1) / H.chunk);
         for (long long o = 0; o < d; o += H.chunk) {
           R.item_pos.push_back(p);
@@ -603,6 +655,9 @@ static void build_rank_plan(const HostPlan& H, int32_t rank, RankPlan& R) {
       }
       R.item_end[c][cls - 1] = (int)R.item_pos.size();
     }
+    R.team_count[c] = (int)R.teams.size() - R.team_first[c];
+    R.team_item_end[c] = (int)R.team_item_pos.size();
+  }
 }
 
 // allocate + upload one rank's session on the CURRENT device
@@ -701,6 +756,28 @@ static int session_from_plan(const HostPlan& H, const RankPlan& R, uint32_t max_
       session_free(s);
       return rc;
     }
+    for (int c = 0; c < 2; c++) {
+      s->n_team_nodes[c] = R.n_team_nodes[c]; s->team_first[c] = R.team_first[c]; s->team_count[c] = R.team_count[c];
+      s->team_item_begin[c] = R.team_item_begin[c]; s->team_item_end[c] = R.team_item_end[c];
+    }
+    if (!R.teams.empty()) {
+      const size_t nti = R.team_item_pos.size(), nt = R.teams.size();
+      // (sized for the 512-thread instantiation: the larger pass-2 allowance per member)
+      s->stage_bytes = (team_stage_bytes<8192, 16384, 4096, 512>() + 255) & ~(size_t)255;
+      if ((rc = dev_alloc(&s->d_team_item_pos, nti)) || (rc = dev_alloc(&s->d_team_item_off, nti)) || (rc = dev_alloc(&s->d_team_item_len, nti)) ||
+          (rc = dev_alloc(&s->d_team_item_team, nti)) || (rc = dev_alloc(&s->d_teams, nt)) || (rc = dev_alloc(&s->d_team_hdr, nt)) ||
+          (rc = dev_alloc(&s->d_stage, nt * s->stage_bytes))) {
+        session_free(s);
+        return rc;
+      }
+      UP(s->d_team_item_pos, R.team_item_pos.data(), nti * sizeof(int));
+      UP(s->d_team_item_off, R.team_item_off.data(), nti * sizeof(long long));
+      UP(s->d_team_item_len, R.team_item_len.data(), nti * sizeof(int));
+      UP(s->d_team_item_team, R.team_item_team.data(), nti * sizeof(int));
+      UP(s->d_teams, R.teams.data(), nt * sizeof(TeamInfo));
+      cudaMemsetAsync(s->d_team_hdr, 0, nt * sizeof(TeamHeader), st);
+      cudaMemsetAsync(s->d_stage, 0, nt * s->stage_bytes, st);  // (the finishing member of a team leaves its staging area clean)
+    }
     UP(s->d_item_pos, R.item_pos.data(), (size_t)s->n_items * sizeof(int));
     UP(s->d_item_off, R.item_off.data(), (size_t)s->n_items * sizeof(long long));
     UP(s->d_item_len, R.item_len.data(), (size_t)s->n_items * sizeof(int));
@@ -731,7 +808,7 @@ static int session_from_plan(const HostPlan& H, const RankPlan& R, uint32_t max_
   s->cur = s->stream;
   if (const char* ev = getenv("PPRB200_OVERLAP")) s->overlap = atoi(ev) != 0;
   s->use_dense = dense_enabled();
-  if (const char* ev = getenv("PPRB200_DENSE_THREADS")) s->dense_threads = atoi(ev) == 512 ? 512 : 1024;
+  if (const char* ev = getenv("PPRB200_DENSE_THREADS")) s->dense_threads = atoi(ev) == 1024 ? 1024 : 512;
   if (getenv("PPRB200_PROF")) {
     if ((rc = dev_alloc(&s->d_prof, (size_t)2 * s->sm_count * 8 * 8))) { session_free(s); return rc; }
     cudaMemsetAsync(s->d_prof, 0, (size_t)2 * s->sm_count * 8 * 8 * sizeof(unsigned long long), st);
@@ -902,16 +979,18 @@ static cudaError_t launch_par(pprb200_session* s, const ParParams& P, int grid) 
   return cudaGetLastError();
 }
 
-template <int H, int R, int TCAP, int CMAX, int COLCAP, int THREADS, int MINB>
+template <int H, int R, int TCAP, int CMAX, int COLCAP, int THREADS, int MINB, bool TEAMS = false>
 static cudaError_t launch_dense(pprb200_session* s, const DenseParams& P, int per_sm) {
   const size_t smem = dense_smem_bytes<H, R, TCAP, CMAX, COLCAP>();
   static bool configured[64] = {false};
   if (!configured[s->device & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(merge_dense_kernel<H, R, TCAP, CMAX, COLCAP, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(merge_dense_kernel<H, R, TCAP, CMAX, COLCAP, THREADS, MINB, TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured[s->device & 63] = true;
   }
-  merge_dense_kernel<H, R, TCAP, CMAX, COLCAP, THREADS, MINB><<<std::min(s->sm_count * per_sm, P.n_items), THREADS, smem, s->cur>>>(P);
+  const int work = P.n_items + (TEAMS ? P.n_team_items : 0);
+  if (work <= 0) return cudaSuccess;
+  merge_dense_kernel<H, R, TCAP, CMAX, COLCAP, THREADS, MINB, TEAMS><<<std::min(s->sm_count * per_sm, work), THREADS, smem, s->cur>>>(P);
   s->launch_count++;
   return cudaGetLastError();
 }
@@ -947,6 +1026,7 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
   for (int cls = 1; cls >= 0; cls--) {
     const int b = s->item_begin[c][cls], e = s->item_end[c][cls];
     if (e == b) continue;
+    const int n_team = (dense && cls == 1) ? s->n_team_nodes[c] : 0;  // leading items that a team of CTAs works on (chunk items below)
     const int n_hub = (dense && cls == 1) ? std::min(s->hub_items[c], e - b) : 0;
     if (!dense || n_hub > 0) {
       const int nb = dense ? n_hub : e - b;
@@ -964,14 +1044,28 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
       if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_par launch failed: %s", cudaGetErrorString(err));
     }
     if (dense && e - b > n_hub) {
+      const int skip = std::max(n_hub, n_team);  // (hubs split for merge_par and team hubs exclude each other: see build_rank_plan)
       DenseParams D;
       std::memset(&D, 0, sizeof(D));
       D.M = P.M;
-      D.item_pos = s->d_item_pos + b + n_hub;
-      D.item_begin = s->d_item_off + b + n_hub;
-      D.item_len = s->d_item_len + b + n_hub;
-      D.n_items = e - b - n_hub;
-      D.item_base = b + n_hub;
+      D.item_pos = s->d_item_pos + b + skip;
+      D.item_begin = s->d_item_off + b + skip;
+      D.item_len = s->d_item_len + b + skip;
+      D.n_items = e - b - skip;
+      D.item_base = b + skip;
+      if (n_team > 0) {
+        const int tb = s->team_item_begin[c];
+        D.team_item_pos = s->d_team_item_pos + tb;
+        D.team_item_begin = s->d_team_item_off + tb;
+        D.team_item_len = s->d_team_item_len + tb;
+        D.team_item_team = s->d_team_item_team + tb;
+        D.n_team_items = s->team_item_end[c] - tb;
+        D.teams = s->d_teams;
+        D.team_hdr = s->d_team_hdr;
+        D.stage = s->d_stage;
+        D.stage_bytes = s->stage_bytes;
+        cudaMemsetAsync(s->d_team_hdr + s->team_first[c], 0, (size_t)s->team_count[c] * sizeof(TeamHeader), cls == 0 ? side : s->stream);
+      }
       D.chunk = s->chunk;
       D.work_idx = 8 + cls;
       D.fb_queue = s->d_fb_queue;
@@ -980,13 +1074,24 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
       s->cur = cls == 0 ? side : s->stream;
       cudaError_t err;
       if (cls == 1) {
-        err = s->dense_threads == 512 ? launch_dense<8192, 16384, 4096, 2048, 1024, 512, 1>(s, D, 1)
-                                      : launch_dense<8192, 16384, 4096, 2048, 1024, 1024, 1>(s, D, 1);
+        err = cudaSuccess;
+        if (D.n_team_items > 0) {  // the hubs' chunk items first, on the instantiation that knows about teams
+          DenseParams T = D;
+          T.n_items = 0;
+          err = s->dense_threads == 512 ? launch_dense<8192, 16384, 4096, 2048, 1024, 512, 1, true>(s, T, 1)
+                                        : launch_dense<8192, 16384, 4096, 2048, 1024, 1024, 1, true>(s, T, 1);
+          D.n_team_items = 0;
+          D.work_idx = 11;  // (its own work counter)
+        }
+        if (err == cudaSuccess)
+          err = s->dense_threads == 512 ? launch_dense<8192, 16384, 4096, 2048, 1024, 512, 1>(s, D, 1)
+                                        : launch_dense<8192, 16384, 4096, 2048, 1024, 1024, 1>(s, D, 1);
       } else {
         static const int cfg = getenv("PPRB200_MID_CFG") ? atoi(getenv("PPRB200_MID_CFG")) : 0;  // A/B hook
         if (cfg == 3) err = launch_dense<2048, 8192, 1024, 512, PAR_MID_MAX, 256, 3>(s, D, 3);
         else if (cfg == 5) err = launch_dense<1024, 4096, 512, 512, PAR_MID_MAX, 128, 5>(s, D, 5);
-        else err = launch_dense<4096, 8192, 2048, 1024, PAR_MID_MAX, 512, 2>(s, D, 2);  // measured best on R-MAT-22 (profiles/r2/sweeps.txt)
+        else if (cfg == 1) err = launch_dense<4096, 8192, 2048, 1024, PAR_MID_MAX, 512, 2>(s, D, 2);
+        else err = launch_dense<4096, 8192, 2048, 1024, PAR_MID_MAX, 256, 2>(s, D, 2);  // measured best on R-MAT-22 (profiles/r2/sweeps.txt)
       }
       if (err != cudaSuccess) return fail(PPRB200_ERR_CUDA, "merge_dense launch failed: %s", cudaGetErrorString(err));
     }
@@ -1369,8 +1474,9 @@ static void preload_kernels() {
   preload(merge_seq_kernel<16384, 1, unsigned short>); preload(merge_seq_kernel<0, 4, unsigned int>);
   preload(merge_par_kernel<8192, 2048, 3072, PAR_CHUNK_MAX, 8192, 512>); preload(merge_par_kernel<2048, 2048, 2048, PAR_MID_MAX, 0, 128>);
   preload(merge_dense_kernel<8192, 16384, 4096, 2048, 1024, 512, 1>); preload(merge_dense_kernel<8192, 16384, 4096, 2048, 1024, 1024, 1>);
+  preload(merge_dense_kernel<8192, 16384, 4096, 2048, 1024, 512, 1, true>); preload(merge_dense_kernel<8192, 16384, 4096, 2048, 1024, 1024, 1, true>);
   preload(merge_dense_kernel<2048, 8192, 1024, 512, PAR_MID_MAX, 256, 3>); preload(merge_dense_kernel<1024, 4096, 512, 512, PAR_MID_MAX, 128, 5>);
-  preload(merge_dense_kernel<4096, 8192, 2048, 1024, PAR_MID_MAX, 512, 2>);
+  preload(merge_dense_kernel<4096, 8192, 2048, 1024, PAR_MID_MAX, 512, 2>); preload(merge_dense_kernel<4096, 8192, 2048, 1024, PAR_MID_MAX, 256, 2>);
   preload(mc_walk_kernel<false, 128>); preload(mc_walk_kernel<false, 256>); preload(mc_walk_kernel<true, 128>); preload(mc_walk_kernel<true, 256>);
   cudaGetLastError();
 }

@@ -104,6 +104,23 @@ def test_hub_split_into_chunks_across_ctas(monkeypatch):
         assert got.stats[k] == want.stats[k], (k, got.stats[k], want.stats[k])
 
 
+@pytest.mark.parametrize("scale,team_deg,team_chunk,it", [(12, 129, 64, 10), (13, 200, 32, 8), (14, 129, 1000, 6)])
+def test_hub_teams_give_the_same_bits_as_single_owner_ctas(monkeypatch, scale, team_deg, team_chunk, it):
+    """merge_dense_kernel's hub teams (a hub's successor list cut into chunks for several CTAs, sums met in a staging area,
+    the last member finishes; pass 2 served by every member) forced onto ordinary nodes: same baskets, same statistics as the
+    oracle -- and hence as the single-CTA path"""
+    monkeypatch.setenv("PPRB200_TEAM_DEG", str(team_deg))
+    monkeypatch.setenv("PPRB200_TEAM_CHUNK", str(team_chunk))
+    g = G.rmat(scale)
+    got, want = run_pair(g, 50, 100, it, 0.85, -1.0, hub=8)
+    assert_bit_identical(got, want, f"hub teams rmat{scale} deg>{team_deg} chunk {team_chunk}")
+    for k in HUB_STAT_KEYS:
+        assert got.stats[k] == want.stats[k], (k, got.stats[k], want.stats[k])
+    monkeypatch.setenv("PPRB200_NO_TEAMS", "1")
+    solo = ppr.grank_csr(g, 50, 100, it, 0.85, -1.0, colour=ppr.find_partitions_csr(g), hub_threshold=8)
+    assert_bit_identical(got, solo, "teams vs single-owner CTAs")
+
+
 def test_two_pass_sketch_path_on_a_large_graph():
     """graphs with more than 16 x 8192 nodes take the sketch-filtered two-pass merge for single-item hubs"""
     g = G.rmat(18)

@@ -132,3 +132,12 @@ def test_l1_error_no_worse_than_the_reference(R, L):
     e_ref = _l1_restricted(ref, g, sources, exact, 50, 0.85)
     print(f"mean restricted L1 (R={R}, L={L}): B200 {e_gpu:.4f}  reference {e_ref:.4f}")
     assert e_gpu <= e_ref * 1.02
+
+
+def test_combine_rounds_with_hub_teams(monkeypatch):
+    """the combine rounds run on the same merge kernels as GRank: hub teams (forced onto ordinary nodes) change nothing"""
+    monkeypatch.setenv("PPRB200_TEAM_DEG", "129")
+    monkeypatch.setenv("PPRB200_TEAM_CHUNK", "48")
+    got, want = run_pair(G.rmat(12), 50, 100, 200, 0.85, 3, hub=8)
+    assert_bit_identical(got, want, "mc with hub teams")
+    assert got.stats["walk_steps"] == want.stats["walk_steps"]
