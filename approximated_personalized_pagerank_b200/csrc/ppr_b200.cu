@@ -1197,7 +1197,6 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
   if (s->world > 1 && !s->attached) return fail(PPRB200_ERR_STATE, "world=%d session: call pprb200_session_ipc_attach before running", s->world);
   s->last_mode = MODE_GRANK;
   s->last_K = K; s->last_L = L; s->last_iterations = iterations;
-  while (s->ev_merge.size() < 2 * (size_t)iterations) { cudaEvent_t e; cudaEventCreate(&e); s->ev_merge.push_back(e); }
   s->merge_launches = 0;
 
   cudaStream_t st = s->stream;
@@ -1231,8 +1230,15 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
       s->launch_count++;
     }
   }
+  // The loop is enqueued without a host round trip per iteration (the convergence test runs on the device and turns
+  // the remaining launches into no-ops). A caller that passes a huge safety bound together with a tolerance should not
+  // pay for millions of such no-ops: after every ENQUEUE_WINDOW iterations the host looks at RunState::active -- the
+  // same value on every rank, it comes out of the barrier's max-reduction -- and stops enqueueing once it is clear.
+  constexpr uint32_t ENQUEUE_WINDOW = 64;
+  uint32_t enqueued = 0;
   for (uint32_t it = 0; it < iterations; it++) {
     const int c = (int)(it & 1);  // partitions.first on even iterations (grank.h:96,129)
+    while (s->ev_merge.size() < 2 * (size_t)(it + 1)) { cudaEvent_t e; cudaEventCreate(&e); s->ev_merge.push_back(e); }
     cudaEventRecord(s->ev_merge[2 * it], st);
     {
       MergeParams Q = P;
@@ -1242,8 +1248,16 @@ static int session_grank_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32
     cudaEventRecord(s->ev_merge[2 * it + 1], st);
     iter_end_kernel<<<1, 1, 0, st>>>(s->d_state, c, tolerance, s->peers);
     s->launch_count++;
+    enqueued = it + 1;
+    if (tolerance >= 0 && enqueued % ENQUEUE_WINDOW == 0 && enqueued < iterations) {
+      int active = 1;
+      cudaError_t e = cudaMemcpyAsync(&active, &s->d_state->active, sizeof(int), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return fail(PPRB200_ERR_CUDA, "run failed: %s", cudaGetErrorString(e));
+      if (!active) break;
+    }
   }
-  s->merge_launches = iterations;
+  s->merge_launches = enqueued;
   if ((rc = enqueue_final(s, (int)L, K, 1.0 - damping))) return rc;
   cudaEventRecord(s->ev_end, st);
   cudaError_t e = cudaGetLastError();
@@ -1281,9 +1295,21 @@ static uint32_t mc_coin_threshold(double damping) {
   return (uint32_t)t;
 }
 
+// MC scores are visits per walk: at most ~1/(1-d) (a walk's expected length), and MC_MAX_STEPS in the worst case. The
+// order-free accumulator of the combine rounds is 2^-59 fixed point in 64 bits, i.e. it holds sums below 16. Up to this
+// damping (1/(1-d) = 8) that leaves a factor of two; above it every node takes the exact-order fp64 path instead.
+constexpr double MC_ORDER_FREE_MAX_DAMPING = 0.875;
+
 static int session_mc_impl(pprb200_session* s, uint32_t K, uint32_t L, uint32_t R, double damping, uint64_t seed, uint32_t rounds) {
   int rc = check_params(K, L, R, damping);
   if (rc) return rc;
+  if (damping > MC_ORDER_FREE_MAX_DAMPING && rounds > 0)
+    for (int c = 0; c < 2; c++)
+      if (s->item_end[c][1] > s->item_begin[c][0])
+        return fail(PPRB200_ERR_PARAM,
+                    "damping %g > %g with order-free nodes in the session: the 2^-59 fixed-point accumulator holds at most 16 visits per "
+                    "walk; create the session with hub_threshold = UINT32_MAX (pprb200_mccompletepathv2 does so by itself)",
+                    damping, MC_ORDER_FREE_MAX_DAMPING);
   if (L > s->max_L) return fail(PPRB200_ERR_PARAM, "L=%u exceeds the session's max_L=%u", L, s->max_L);
   L = effective_L(L, s->n);
   if ((size_t)roundup4((int)L) * 12 > 200 * 1024) return fail(PPRB200_ERR_PARAM, "min(L, n)=%u is above this build's limit of 17064", L);
@@ -2031,6 +2057,7 @@ int pprb200_mccompletepathv2(const int64_t* row_ptr, const int32_t* col, int32_t
   OneShot job;
   job.mode = MODE_MC; job.K = K; job.L = L; job.iterations = R; job.damping = damping; job.tolerance = 0.0;
   job.seed = seed; job.rounds = rounds;
+  if (damping > MC_ORDER_FREE_MAX_DAMPING) hub_threshold = UINT32_MAX;  // (see MC_ORDER_FREE_MAX_DAMPING)
   std::lock_guard<std::mutex> lk(g_api_mutex);
   return run_oneshot(row_ptr, col, n, nullptr, hub_threshold, job, out_ids, out_scores, out_cnt, stats);
 }

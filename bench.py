@@ -193,7 +193,8 @@ def reference_sample(w, g, cores, steps=1, warm=0, allow_reference=True):
         note = "full job" if full else f"bounded sample: iterations={it} of {w['iterations']} (extrapolated, BASELINE.md 3)"
         return sum(units), sum(times), kind, cores, sample, note
     # MC: the reference is single-threaded by construction; hops are counted by the port at the same walk budget
-    R = w["iterations"] if full else min(w["iterations"], REFERENCE_MC_SAMPLE_R)
+    # (bounded: R = 50 on a million nodes is ~12 s on 16 threads; larger graphs get proportionally fewer walks per source)
+    R = w["iterations"] if full else max(2, min(w["iterations"], REFERENCE_MC_SAMPLE_R * (1 << 20) // max(g.n, 1 << 20)))
     use_ref = have_ref
     kind = "reference" if use_ref else "port"
     hops = ob.oracle_mc(g, w["K"], w["L"], R, w["damping"], 1, 0, nthreads=cores).stats["walk_steps"]
@@ -425,7 +426,8 @@ def run_job(w, wname, args, cx, steps, warm, hub_threshold, want_e2e=True, want_
         roofline["walk_steps_per_s_walk_kernel_only"] = hops / (walk_ms / 1e3) if walk_ms > 0 else None
         roofline["sector_granular"] = {"bytes_per_hop": 64, "achieved": (64.0 * hops / 1e9) / (walk_ms / 1e3) if walk_ms > 0 else None,
                                        "unit": "GB/s", "frac_of_hbm_peak": (64.0 * hops / 1e9) / (walk_ms / 1e3) / peak if walk_ms > 0 else None,
-                                       "note": "the scale-20 CSR (71 MB) is L2-resident: the walk is bound by dependent L2 gathers, not by HBM"}
+                                       "note": (f"CSR of this graph: {(4 * g.n_edges + 8 * g.n) / 1e6:.0f} MB against 126 MB of L2; "
+                                                "the walk is bound by two dependent gathers per hop, not by HBM bandwidth")}
         roofline["l2_throughput"] = prof.get("l2") if prof else None
     out = {
         "metric": metric, "value": units / (dev_ms / 1e3), "unit": unit, "n_gpus": world, "steps": steps, "warmup": warm,
@@ -533,7 +535,8 @@ def main():
         del cx.flush
         torch.cuda.empty_cache()
         cx.lib.pprb200_release_cached_memory()  # the C++ program below is another process: give it the GPU's memory
-        line["e2e_api"] = e2e_api_cpp(args.workload)
+        # (tests/cpp/api_bench.cc builds R-MAT graphs as std::unordered_map and calls ppr::grank: GRank R-MAT workloads only)
+        line["e2e_api"] = e2e_api_cpp(args.workload) if (w["kind"] == "grank" and w["gen"] == "rmat") else None
     try:
         line["parity_report"] = json.loads((ROOT / "profiles" / "r2" / "parity_report.json").read_text())
     except Exception:

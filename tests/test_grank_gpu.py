@@ -165,6 +165,24 @@ def test_convergence_stops_at_the_same_iteration(tol):
     assert_bit_identical(got, want, f"tol {tol}")
 
 
+def test_huge_iteration_bound_with_a_tolerance_costs_only_what_ran():
+    """A caller's safety bound of a million iterations must not enqueue a million no-op sweeps: the loop is enqueued in
+    windows and stops once the device-side convergence flag is clear (the reference stops at convergence, grank.h:92)"""
+    import time
+    rng = np.random.default_rng(5)
+    g = G.from_edges(300, rng.integers(0, 300, 2000), rng.integers(0, 300, 2000))
+    t0 = time.perf_counter()
+    got, want = run_pair(g, 300, 300, 1_000_000, 0.85, 1e-5)
+    sec = time.perf_counter() - t0
+    assert 64 < got.stats["iterations_run"] == want.stats["iterations_run"] < 1000   # (converges in the second window)
+    assert_bit_identical(got, want, "1e6 iterations bound")
+    assert sec < 30, sec     # (a million enqueued sweeps of ~20 launches each take minutes)
+    # a bound that is actually needed runs through several windows
+    got, want = run_pair(g, 300, 300, 200, 0.85, 0.0)
+    assert got.stats["iterations_run"] == want.stats["iterations_run"]
+    assert_bit_identical(got, want, "200 iterations, tolerance 0")
+
+
 def test_single_iteration_and_two_iterations():
     g = G.rmat(9)
     for it in (1, 2, 3):

@@ -56,6 +56,43 @@ def test_damping_one_hits_the_step_cap():
     assert_bit_identical(got, want, "d=1 ring")
 
 
+@pytest.mark.parametrize("damping", [0.99, 1.0])
+def test_high_damping_on_a_clique_with_self_loops_stays_in_range(damping):
+    """Visits per walk reach 1/(1-d) (d = 1: the 4096-hop cap) -- far above the 16 that the order-free 2^-59 accumulator of
+    the combine rounds can hold. With the DEFAULT hub threshold (out-degree 20 > 12 would be order-free) the one-shot call
+    must route every node to the exact-order fp64 path: bit-identical to the oracle's exact-order result, no wrap-around."""
+    n = 20
+    src = np.repeat(np.arange(n), n)
+    dst = np.tile(np.arange(n), n)          # complete digraph with self loops, out-degree 20
+    g = G.from_edges(n, src, dst)
+    got = ppr.mccompletepathv2_csr(g, 10, 20, 50, damping, seed=SEED, rounds=2, hub_threshold=0)
+    want = ob.oracle_mc(g, 10, 20, 50, damping, SEED, 2, hub_threshold=0)
+    assert_bit_identical(got, want, f"mc clique d={damping}")
+    if damping == 1.0:
+        assert got.scores.max() > 16.0       # the range the fixed-point words would have wrapped at
+    assert np.isfinite(got.scores).all() and (got.scores >= 0).all()
+
+
+def test_session_refuses_high_damping_when_it_holds_order_free_nodes():
+    from approximated_personalized_pagerank_b200._lib import PprB200Error
+    n = 20
+    g = G.from_edges(n, np.repeat(np.arange(n), n), np.tile(np.arange(n), n))
+    s = ppr.Session(g, max_L=20, hub_threshold=0)
+    try:
+        with pytest.raises(PprB200Error, match="fixed-point accumulator"):
+            s.mc(10, 20, 50, 0.99, seed=SEED, rounds=2)
+        s.mc(10, 20, 50, 0.85, seed=SEED, rounds=2)   # fine below the limit
+        s.fetch()
+    finally:
+        s.close()
+    s = ppr.Session(g, max_L=20, hub_threshold=ppr.NEVER_HUB)
+    try:
+        s.mc(10, 20, 50, 0.99, seed=SEED, rounds=2)
+        s.fetch()
+    finally:
+        s.close()
+
+
 def test_seed_changes_the_walks_and_runs_repeat():
     g = G.rmat(10)
     a = ppr.mccompletepathv2_csr(g, 50, 100, 100, 0.85, seed=1, rounds=0)
