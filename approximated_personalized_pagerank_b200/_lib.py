@@ -82,6 +82,7 @@ def load():
     lib.pprb200_last_error.restype = C.c_char_p
     lib.pprb200_device_count.restype = c_int
     lib.pprb200_find_partitions.argtypes = [c_void_p, c_void_p, c_int32, c_void_p]
+    lib.pprb200_find_partitions_device.argtypes = [c_void_p, c_void_p, c_int32, c_void_p]
     lib.pprb200_grank.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_uint32, c_uint32, c_uint32, c_double, c_double,
                                   c_uint32, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.pprb200_mccompletepathv2.argtypes = [c_void_p, c_void_p, c_int32, c_uint32, c_uint32, c_uint32, c_double, c_uint64,
@@ -106,7 +107,7 @@ def load():
     lib.pprb200_shard_owner.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_uint32, c_int32, c_void_p]
     lib.pprb200_gen_rmat.argtypes = [c_uint32, c_uint32, c_uint64, c_double, c_double, c_double, c_void_p, c_void_p]
     lib.pprb200_gen_ba.argtypes = [c_int32, c_uint32, c_uint64, c_void_p, c_void_p, C.POINTER(c_int64)]
-    for name in ("pprb200_find_partitions", "pprb200_grank", "pprb200_mccompletepathv2", "pprb200_session_create",
+    for name in ("pprb200_find_partitions", "pprb200_find_partitions_device", "pprb200_grank", "pprb200_mccompletepathv2", "pprb200_session_create",
                  "pprb200_session_grank", "pprb200_session_mc", "pprb200_session_fetch", "pprb200_session_stats",
                  "pprb200_session_kernel_time", "pprb200_gen_rmat", "pprb200_gen_ba", "pprb200_session_ipc_export",
                  "pprb200_session_ipc_attach", "pprb200_shard_owner"):

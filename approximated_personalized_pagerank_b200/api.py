@@ -56,11 +56,13 @@ class Baskets:
         return out
 
 
-def find_partitions_csr(g: CSRGraph) -> np.ndarray:
-    """colour[v] = 0 (partitions.first) / 1 (partitions.second); pprInternal.h:29-99."""
+def find_partitions_csr(g: CSRGraph, device: bool = False) -> np.ndarray:
+    """colour[v] = 0 (partitions.first) / 1 (partitions.second); pprInternal.h:29-99. device=True: the large component is
+    levelled on the GPU, as the session / one-shot entry points do for graphs of a million edges and more (same output)."""
     lib = _lib.load()
     colour = np.zeros(max(g.n, 1), dtype=np.uint8)
-    _lib.check(lib.pprb200_find_partitions(_lib.ptr(g.row_ptr), _lib.ptr(g.col), g.n, _lib.ptr(colour)))
+    fn = lib.pprb200_find_partitions_device if device else lib.pprb200_find_partitions
+    _lib.check(fn(_lib.ptr(g.row_ptr), _lib.ptr(g.col), g.n, _lib.ptr(colour)))
     return colour[:g.n]
 
 

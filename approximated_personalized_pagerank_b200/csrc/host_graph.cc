@@ -242,7 +242,7 @@ void host_transpose(const int64_t* row_ptr, const int32_t* col, int32_t n, std::
 // it), whatever the visiting order inside a level: the colouring below is level-synchronous, and the
 // levels of large components are expanded by all host threads. oracle/ppr_oracle.c keeps the literal FIFO version;
 // tests/test_host_logic.py compares the two.
-int find_partitions(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8_t* colour) {
+int find_partitions(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8_t* colour, const ComponentFn* device_component) {
   if (n == 0) return PPRB200_OK;
   const bool timing = getenv("PPRB200_HOST_TIMING") != nullptr;
   auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -262,7 +262,7 @@ int find_partitions(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8
   // of the still-unseen nodes (parallel over node ranges, no atomics: a thread writes only its own nodes). The scanned edges
   // are budgeted at 4 E; a component that needs more levels than that (a long chain) continues in phase B.
   double t_a = t_begin;
-  const bool phase_a = e >= (1 << 17);
+  const bool phase_a = e >= (1 << 17) || device_component != nullptr;
   if (phase_a) {
     if (row_ptr[1] == row_ptr[0]) {  // node 0 has no out-edges: in-degrees tell isolated roots from sink roots
       std::vector<uint32_t> indeg((size_t)n);
@@ -272,7 +272,9 @@ int find_partitions(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8
         colour[first_root++] = 0;
       }
     }
-    if (first_root < n) {
+    if (first_root < n && device_component && (*device_component)(first_root, seen.data(), colour)) {
+      first_root++;  // (the session entry points: this component -- nearly every edge -- was levelled on the device, plan_device.cuh)
+    } else if (first_root < n) {
       seen[(size_t)first_root] = 2;
       colour[first_root] = 0;
       frontier.assign(1, first_root);

@@ -18,6 +18,7 @@
 #include "ppr_exact.cuh"
 #include "merge_par.cuh"
 #include "merge_dense.cuh"
+#include "plan_device.cuh"
 #include "ppr_internal.h"
 
 namespace pprb200 {
@@ -391,6 +392,44 @@ static int default_chunk(int32_t n, int world) {
   return c;
 }
 
+// Stable counting sort of the nodes 0..n-1 on a small key, on all host threads: every thread counts a contiguous id range
+// into its own histogram, an exclusive scan in (key, thread) order turns the counts into write offsets, and the same ranges
+// scatter. Ties keep ascending id order whatever the thread count (ranges are contiguous and scanned in order).
+// key(v) < K, or SORT_SKIP to leave the node out. start[k] = first output index of key k (start[K] = total).
+constexpr uint32_t SORT_SKIP = 0xFFFFFFFFu;
+template <typename KeyFn>
+static void parallel_counting_sort(int32_t n, size_t K, KeyFn key, std::vector<int32_t>& start, std::vector<int32_t>& out) {
+  const int parts = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), ((int64_t)n + (1 << 16) - 1) >> 16));
+  std::vector<std::vector<int32_t>> hist((size_t)parts);
+  host_parallel(parts, [&](int t) {
+    std::vector<int32_t>& h = hist[(size_t)t];
+    h.assign(K, 0);
+    for (int64_t v = (int64_t)n * t / parts, hi = (int64_t)n * (t + 1) / parts; v < hi; v++) {
+      const uint32_t k = key((int32_t)v);
+      if (k != SORT_SKIP) h[k]++;
+    }
+  });
+  start.assign(K + 1, 0);
+  int32_t run = 0;
+  for (size_t k = 0; k < K; k++) {
+    start[k] = run;
+    for (int t = 0; t < parts; t++) { const int32_t c = hist[(size_t)t][k]; hist[(size_t)t][k] = run; run += c; }
+  }
+  start[K] = run;
+  out.assign((size_t)run, 0);
+  host_parallel(parts, [&](int t) {
+    std::vector<int32_t>& h = hist[(size_t)t];
+    for (int64_t v = (int64_t)n * t / parts, hi = (int64_t)n * (t + 1) / parts; v < hi; v++) {
+      const uint32_t k = key((int32_t)v);
+      if (k != SORT_SKIP) out[(size_t)h[k]++] = (int32_t)v;
+    }
+  });
+}
+
+// degrees up to SORT_DEG_CAP - 2 get a counting-sort key of their own; the few nodes above share the first key of their
+// group and are put in order by a comparison sort afterwards (power-law graphs: thousands of nodes, not millions)
+constexpr int64_t SORT_DEG_CAP = 4096;
+
 // storage positions of the non-sink nodes: colour-major, then class (0 exact-order, 1 mid, 2 big), then out-degree
 // descending (ties by dense id)
 // owner_of_pos (world > 1): longest-processing-time-first over each (colour, class) list, work = out-degree, so that
@@ -398,31 +437,27 @@ static int default_chunk(int32_t n, int world) {
 static void storage_order(const int64_t* row_ptr, int32_t n, const uint8_t* colour, uint32_t hub_threshold, int mid_deg,
                           std::vector<int32_t>& order, int cls_begin[2][3], int cls_end[2][3], int world = 1,
                           std::vector<int32_t>* owner_of_pos = nullptr) {
-  // one counting sort on the key (colour, class, out-degree descending); nodes are scattered in ascending id order, so
-  // ties keep it
-  int64_t max_d = 0;
-  for (int32_t v = 0; v < n; v++) max_d = std::max<int64_t>(max_d, row_ptr[v + 1] - row_ptr[v]);
-  const size_t per_group = (size_t)max_d + 1;
-  std::vector<int32_t> start(6 * per_group + 1, 0);
-  auto key_of = [&](int32_t v, int64_t d) -> size_t {
-    const int cls = (uint64_t)d <= (uint64_t)hub_threshold ? 0 : (d <= mid_deg ? 1 : 2);
-    return ((size_t)colour[v] * 3 + (size_t)cls) * per_group + (size_t)(max_d - d);
-  };
-  for (int32_t v = 0; v < n; v++) {
+  // key = (colour, class, out-degree descending): slot 0 of a group = "SORT_DEG_CAP - 1 successors or more"
+  const size_t per_group = (size_t)SORT_DEG_CAP;
+  auto key_of = [&](int32_t v) -> uint32_t {
     const int64_t d = row_ptr[v + 1] - row_ptr[v];
-    if (d > 0) start[key_of(v, d) + 1]++;
-  }
-  for (size_t i = 0; i < 6 * per_group; i++) start[i + 1] += start[i];
+    if (d <= 0) return SORT_SKIP;
+    const int cls = (uint64_t)d <= (uint64_t)hub_threshold ? 0 : (d <= mid_deg ? 1 : 2);
+    const int64_t dd = std::min<int64_t>(d, SORT_DEG_CAP - 1);
+    return (uint32_t)(((size_t)colour[v] * 3 + (size_t)cls) * per_group + (size_t)(SORT_DEG_CAP - 1 - dd));
+  };
+  std::vector<int32_t> start;
+  parallel_counting_sort(n, 6 * per_group, key_of, start, order);
   for (int c = 0; c < 2; c++)
     for (int cls = 0; cls < 3; cls++) {
-      cls_begin[c][cls] = start[((size_t)c * 3 + (size_t)cls) * per_group];
-      cls_end[c][cls] = start[((size_t)c * 3 + (size_t)cls + 1) * per_group];
+      const size_t g = (size_t)c * 3 + (size_t)cls;
+      cls_begin[c][cls] = start[g * per_group];
+      cls_end[c][cls] = start[(g + 1) * per_group];
+      // the group's large nodes (all under its first key, in id order): out-degree descending, ties by id
+      std::stable_sort(order.begin() + start[g * per_group], order.begin() + start[g * per_group + 1], [&](int32_t a, int32_t b) {
+        return row_ptr[a + 1] - row_ptr[a] > row_ptr[b + 1] - row_ptr[b];
+      });
     }
-  order.assign((size_t)start[6 * per_group], 0);
-  for (int32_t v = 0; v < n; v++) {
-    const int64_t d = row_ptr[v + 1] - row_ptr[v];
-    if (d > 0) order[(size_t)start[key_of(v, d)]++] = v;
-  }
   if (owner_of_pos) {
     owner_of_pos->assign(order.size(), 0);
     if (world > 1)
@@ -469,9 +504,93 @@ struct HostPlan {
   std::vector<int32_t> order, owner_of_pos, dense_of, rank_of, pos_of, label;
   std::vector<long long> row_off;
   std::vector<unsigned long long> rowdeg;
-  std::vector<uint32_t> enc;
+  std::vector<uint32_t> enc;     // column words in storage order -- on the host (small graphs, pprb200_debug_host_plan) ...
+  uint32_t* d_enc = nullptr;     // ... or produced on the device (plan_device.cuh): then `enc` stays empty
+  int enc_device = 0;
   double prep_ms = 0;
+  HostPlan() = default;
+  HostPlan(const HostPlan&) = delete;
+  HostPlan& operator=(const HostPlan&) = delete;
+  ~HostPlan() {
+    if (d_enc) {
+      int cur = 0;
+      cudaGetDevice(&cur);
+      cudaSetDevice(enc_device);
+      cudaFree(d_enc);
+      cudaSetDevice(cur);
+    }
+  }
 };
+
+// The caller's CSR on the device while the plan is made: the colouring BFS and the column-word encode read it there
+// (plan_device.cuh). Allocated with plain cudaMalloc/cudaFree on the legacy stream: a plan is made once per call.
+struct RawCsrDev {
+  long long* row_ptr = nullptr;
+  int* col = nullptr;
+  int32_t n = 0;
+  int64_t E = 0;
+  int device = 0;
+  bool ok = false;
+  ~RawCsrDev() { release(); }
+  void release() {
+    if (row_ptr) cudaFreeAsync(row_ptr, 0);
+    if (col) cudaFreeAsync(col, 0);
+    row_ptr = nullptr; col = nullptr; ok = false;
+  }
+  bool upload(const int64_t* h_row_ptr, const int32_t* h_col, int32_t n_, int64_t E_) {
+    n = n_; E = E_;
+    cudaGetDevice(&device);
+    if (cudaMallocAsync((void**)&row_ptr, ((size_t)n + 1) * sizeof(long long), 0) != cudaSuccess ||
+        cudaMallocAsync((void**)&col, (size_t)std::max<int64_t>(E, 1) * sizeof(int), 0) != cudaSuccess ||
+        cudaMemcpyAsync(row_ptr, h_row_ptr, ((size_t)n + 1) * sizeof(long long), cudaMemcpyHostToDevice, 0) != cudaSuccess ||
+        cudaMemcpyAsync(col, h_col, (size_t)E * sizeof(int), cudaMemcpyHostToDevice, 0) != cudaSuccess) {
+      cudaGetLastError();
+      release();
+      return false;
+    }
+    ok = true;
+    return true;
+  }
+};
+
+// find_partitions' device_component: level-synchronous BFS of root's component, one launch per level
+static bool device_component(const RawCsrDev& G, int32_t root, uint8_t* seen, uint8_t* colour) {
+  const int32_t n = G.n;
+  unsigned char* d_level = nullptr;
+  unsigned int* d_changed = nullptr;
+  if (cudaMallocAsync((void**)&d_level, (size_t)n, 0) != cudaSuccess || cudaMallocAsync((void**)&d_changed, sizeof(unsigned int), 0) != cudaSuccess) {
+    cudaGetLastError();
+    if (d_level) cudaFreeAsync(d_level, 0);
+    return false;
+  }
+  int sm = 148;
+  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, G.device);
+  cudaMemsetAsync(d_level, BFS_UNSEEN, (size_t)n, 0);
+  cudaMemsetAsync(d_level + root, 0, 1, 0);
+  int cur = 0;
+  bool ok = true;
+  for (; cur < BFS_MAX_LEVEL; cur++) {
+    unsigned int changed = 0;
+    cudaMemsetAsync(d_changed, 0, sizeof(unsigned int), 0);
+    bfs_level_kernel<<<sm * 8, 256, 0, 0>>>(G.row_ptr, G.col, n, d_level, (unsigned char)cur, d_changed);
+    if (cudaMemcpyAsync(&changed, d_changed, sizeof(unsigned int), cudaMemcpyDeviceToHost, 0) != cudaSuccess || cudaStreamSynchronize(0) != cudaSuccess) { ok = false; break; }
+    if (!changed) break;
+  }
+  if (cur >= BFS_MAX_LEVEL) ok = false;  // a long chain: the host's frontier-based BFS does this one
+  if (ok) {
+    std::vector<unsigned char> level((size_t)n);
+    ok = cudaMemcpyAsync(level.data(), d_level, (size_t)n, cudaMemcpyDeviceToHost, 0) == cudaSuccess && cudaStreamSynchronize(0) == cudaSuccess;
+    if (ok)
+      host_parallel_for(n, 1 << 16, [&](int, int64_t lo, int64_t hi) {
+        for (int64_t v = lo; v < hi; v++)
+          if (level[(size_t)v] != BFS_UNSEEN) { seen[v] = 1; colour[v] = (uint8_t)(level[(size_t)v] & 1u); }
+      });
+  }
+  cudaGetLastError();
+  cudaFreeAsync(d_level, 0);
+  cudaFreeAsync(d_changed, 0);
+  return ok;
+}
 
 constexpr int SEQ_SMALL_DEG = 3;  // exact-order nodes up to this out-degree fit 512-slot tables: twice the warps per SM
 
@@ -504,8 +623,10 @@ static int team_chunk_len() {
   return 8192;
 }
 
+// use_device: the edge-sized parts of the plan (colouring BFS of the large component, column words) run on the current
+// device when the graph is large enough to pay for the upload; pprb200_debug_host_plan (no device) keeps everything here
 static int build_host_plan(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour_in, uint32_t hub_threshold,
-                           int32_t world, bool need_colour, HostPlan& H) {
+                           int32_t world, bool need_colour, HostPlan& H, bool use_device = false) {
   const double t0 = now_ms();
   int rc;
   H.n = n;
@@ -513,8 +634,13 @@ static int build_host_plan(const int64_t* row_ptr, const int32_t* col, int32_t n
   H.hub_threshold = hub_threshold == 0 ? PPRB200_DEFAULT_HUB_THRESHOLD : hub_threshold;
   H.colour.assign((size_t)n, 0);
   std::vector<uint8_t>& colour = H.colour;
+  RawCsrDev G;
+  if (use_device && row_ptr[n] >= (1ll << 20) && !getenv("PPRB200_HOST_PLAN")) G.upload(row_ptr, col, n, row_ptr[n]);
   if (colour_in) std::memcpy(colour.data(), colour_in, (size_t)n);
-  else if (need_colour && (rc = find_partitions(row_ptr, col, n, colour.data()))) return rc;  // (MC-only session: one class)
+  else if (need_colour) {  // (MC-only session: one class)
+    const ComponentFn on_device = [&](int32_t root, uint8_t* seen, uint8_t* col_out) { return device_component(G, root, seen, col_out); };
+    if ((rc = find_partitions(row_ptr, col, n, colour.data(), G.ok ? &on_device : nullptr))) return rc;
+  }
   for (int32_t v = 0; v < n; v++) {
     if (colour[v] > 1) return fail(PPRB200_ERR_PARAM, "colour[%d] = %d is not 0/1", v, colour[v]);
     H.colour_count[colour[v]]++;
@@ -528,55 +654,104 @@ static int build_host_plan(const int64_t* row_ptr, const int32_t* col, int32_t n
   const std::vector<int32_t>& order = H.order;
   const double t_ord = now_ms();
   // rank labels: in-degree descending, ties by dense id (the keys stored in the baskets) -- a counting sort
-  H.dense_of.assign((size_t)n, 0);
   H.rank_of.assign((size_t)n, 0);
   {
     std::vector<uint32_t> indeg((size_t)n);
     host_indegree(col, row_ptr[n], n, indeg.data());
-    uint32_t max_in = 0;
-    for (int32_t v = 0; v < n; v++) max_in = std::max(max_in, indeg[(size_t)v]);
-    std::vector<int32_t> start((size_t)max_in + 2, 0);
-    for (int32_t v = 0; v < n; v++) start[(size_t)(max_in - indeg[(size_t)v]) + 1]++;
-    for (size_t i = 0; i <= (size_t)max_in; i++) start[i + 1] += start[i];
-    for (int32_t v = 0; v < n; v++) {
-      const int32_t r = start[(size_t)(max_in - indeg[(size_t)v])]++;
-      H.dense_of[(size_t)r] = v;
-      H.rank_of[(size_t)v] = r;
-    }
+    std::vector<int32_t> start;
+    parallel_counting_sort(n, (size_t)SORT_DEG_CAP, [&](int32_t v) -> uint32_t {
+      return (uint32_t)(SORT_DEG_CAP - 1 - (int64_t)std::min<uint32_t>(indeg[(size_t)v], (uint32_t)(SORT_DEG_CAP - 1)));
+    }, start, H.dense_of);
+    std::stable_sort(H.dense_of.begin(), H.dense_of.begin() + start[1], [&](int32_t a, int32_t b) { return indeg[(size_t)a] > indeg[(size_t)b]; });
+    host_parallel_for(n, 1 << 16, [&](int, int64_t lo, int64_t hi) {
+      for (int64_t r = lo; r < hi; r++) H.rank_of[(size_t)H.dense_of[(size_t)r]] = (int32_t)r;
+    });
   }
   const double t_rank = now_ms();
   const int32_t M = (int32_t)order.size();
   H.M = M;
   H.pos_of.assign((size_t)n, -1);
-  for (int32_t p = 0; p < M; p++) H.pos_of[order[p]] = p;
   H.row_off.assign((size_t)M + 1, 0);
   H.rowdeg.assign((size_t)std::max(M, 1), 0ull);
   H.label.assign((size_t)std::max(M, 1), 0);
-  for (int32_t p = 0; p < M; p++) {
-    const int64_t d = row_ptr[order[p] + 1] - row_ptr[order[p]];
-    H.row_off[(size_t)p + 1] = H.row_off[p] + d;
-    if (d > H.max_deg) H.max_deg = (int32_t)std::min<int64_t>(d, INT32_MAX);
-    if ((unsigned long long)d >> ROWDEG_SHIFT || (unsigned long long)H.row_off[p] >> (64 - ROWDEG_SHIFT))
-      return fail(PPRB200_ERR_GRAPH, "out-degree %lld / edge offset %lld exceed the packed row word (2^%d successors per node, 2^%d edges)",
-                  (long long)d, H.row_off[p], ROWDEG_SHIFT, 64 - ROWDEG_SHIFT);
-    H.rowdeg[(size_t)p] = ((unsigned long long)H.row_off[p] << ROWDEG_SHIFT) | (unsigned long long)d;
-    H.label[(size_t)p] = H.rank_of[order[p]];
+  {
+    // offsets in storage order: per-range sums, a scan over the ranges, then every range writes its part
+    const int parts = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), ((int64_t)M + (1 << 16) - 1) >> 16));
+    std::vector<long long> base((size_t)parts + 1, 0);
+    std::vector<long long> part_max((size_t)parts, 0);
+    host_parallel(parts, [&](int t) {
+      long long sum = 0, mx = 0;
+      for (int64_t p = (int64_t)M * t / parts, hi = (int64_t)M * (t + 1) / parts; p < hi; p++) {
+        const int64_t d = row_ptr[order[(size_t)p] + 1] - row_ptr[order[(size_t)p]];
+        sum += d;
+        mx = std::max<long long>(mx, d);
+      }
+      base[(size_t)t + 1] = sum;
+      part_max[(size_t)t] = mx;
+    });
+    long long max_d = 0;
+    for (int t = 0; t < parts; t++) { base[(size_t)t + 1] += base[(size_t)t]; max_d = std::max(max_d, part_max[(size_t)t]); }
+    H.max_deg = (int32_t)std::min<long long>(max_d, INT32_MAX);
+    if ((unsigned long long)max_d >> ROWDEG_SHIFT || (unsigned long long)base[(size_t)parts] >> (64 - ROWDEG_SHIFT))
+      return fail(PPRB200_ERR_GRAPH, "out-degree %lld / edge count %lld exceed the packed row word (2^%d successors per node, 2^%d edges)",
+                  max_d, base[(size_t)parts], ROWDEG_SHIFT, 64 - ROWDEG_SHIFT);
+    host_parallel(parts, [&](int t) {
+      long long off = base[(size_t)t];
+      for (int64_t p = (int64_t)M * t / parts, hi = (int64_t)M * (t + 1) / parts; p < hi; p++) {
+        const int32_t v = order[(size_t)p];
+        const int64_t d = row_ptr[v + 1] - row_ptr[v];
+        H.pos_of[(size_t)v] = (int32_t)p;
+        H.row_off[(size_t)p] = off;
+        H.rowdeg[(size_t)p] = ((unsigned long long)off << ROWDEG_SHIFT) | (unsigned long long)d;
+        H.label[(size_t)p] = H.rank_of[(size_t)v];
+        off += d;
+      }
+    });
+    H.row_off[(size_t)M] = base[(size_t)parts];
   }
   const int64_t E = H.row_off[M];
   H.E = E;
-  for (int c = 0; c < 2; c++)
-    for (int p = H.cls_begin[c][0]; p < H.cls_end[c][0]; p++)
+  for (int c = 0; c < 2; c++)  // (a class is stored by out-degree descending: its first node has the largest)
+    if (H.cls_end[c][0] > H.cls_begin[c][0]) {
+      const int p = H.cls_begin[c][0];
       H.max_deg_seq = std::max<int32_t>(H.max_deg_seq, (int32_t)std::min<long long>(H.row_off[(size_t)p + 1] - H.row_off[p], INT32_MAX));
+    }
   const double t_off = now_ms();
-  // column words: one lookup table (word of every node), then a parallel gather over edge-balanced position ranges
-  H.enc.assign((size_t)std::max<int64_t>(E, 1), 0u);
-  {
-    std::vector<uint32_t> word_of((size_t)n);
-    host_parallel_for(n, 1 << 15, [&](int, int64_t lo, int64_t hi) {
-      for (int64_t v = lo; v < hi; v++)
-        word_of[(size_t)v] = H.pos_of[(size_t)v] < 0 ? (COL_SINK | (uint32_t)H.rank_of[(size_t)v])
-                                                      : ((uint32_t)H.pos_of[(size_t)v] | ((uint32_t)colour[(size_t)v] << COL_COLOUR_SHIFT));
-    });
+  // column words: one lookup table (word of every node), then a gather -- on the device over the uploaded CSR, or here in
+  // parallel over edge-balanced position ranges
+  std::vector<uint32_t> word_of((size_t)n);
+  host_parallel_for(n, 1 << 15, [&](int, int64_t lo, int64_t hi) {
+    for (int64_t v = lo; v < hi; v++)
+      word_of[(size_t)v] = H.pos_of[(size_t)v] < 0 ? (COL_SINK | (uint32_t)H.rank_of[(size_t)v])
+                                                    : ((uint32_t)H.pos_of[(size_t)v] | ((uint32_t)colour[(size_t)v] << COL_COLOUR_SHIFT));
+  });
+  bool encoded = false;
+  if (G.ok && M > 0 && E > 0) {
+    int* d_order = nullptr;
+    long long* d_off = nullptr;
+    unsigned int* d_word = nullptr;
+    H.enc_device = G.device;
+    int sm = 148;
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, G.device);
+    if (cudaMalloc((void**)&H.d_enc, (size_t)E * sizeof(uint32_t)) == cudaSuccess &&
+        cudaMallocAsync((void**)&d_order, (size_t)M * sizeof(int), 0) == cudaSuccess &&
+        cudaMallocAsync((void**)&d_off, ((size_t)M + 1) * sizeof(long long), 0) == cudaSuccess &&
+        cudaMallocAsync((void**)&d_word, (size_t)n * sizeof(unsigned int), 0) == cudaSuccess &&
+        cudaMemcpyAsync(d_order, order.data(), (size_t)M * sizeof(int), cudaMemcpyHostToDevice, 0) == cudaSuccess &&
+        cudaMemcpyAsync(d_off, H.row_off.data(), ((size_t)M + 1) * sizeof(long long), cudaMemcpyHostToDevice, 0) == cudaSuccess &&
+        cudaMemcpyAsync(d_word, word_of.data(), (size_t)n * sizeof(unsigned int), cudaMemcpyHostToDevice, 0) == cudaSuccess) {
+      encode_kernel<<<sm * 8, 256, 0, 0>>>(G.row_ptr, G.col, d_order, d_off, d_word, M, H.d_enc);
+      encoded = cudaGetLastError() == cudaSuccess && cudaStreamSynchronize(0) == cudaSuccess;
+    }
+    cudaGetLastError();
+    if (d_order) cudaFreeAsync(d_order, 0);
+    if (d_off) cudaFreeAsync(d_off, 0);
+    if (d_word) cudaFreeAsync(d_word, 0);
+    if (!encoded && H.d_enc) { cudaFree(H.d_enc); H.d_enc = nullptr; }
+  }
+  G.release();
+  if (!encoded) {
+    H.enc.assign((size_t)std::max<int64_t>(E, 1), 0u);
     const int parts = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), E / (1 << 15)));
     host_parallel(parts, [&](int t) {
       const int32_t p_lo = (int32_t)(std::lower_bound(H.row_off.begin(), H.row_off.end(), (long long)(E * t / parts)) - H.row_off.begin());
@@ -661,8 +836,10 @@ static void build_rank_plan(const HostPlan& H, int32_t rank, RankPlan& R) {
 }
 
 // allocate + upload one rank's session on the CURRENT device
+// `src`: a session of the same plan on ANOTHER device of this process (peer access enabled): the rank-independent arrays
+// -- CSR, labels, maps, 0.33 GB on R-MAT-22 -- are then copied from there over NVLink instead of crossing PCIe once per GPU
 static int session_from_plan(const HostPlan& H, const RankPlan& R, uint32_t max_L, int32_t rank, void* stream, bool ipc,
-                             pprb200_session** out) {
+                             pprb200_session** out, const pprb200_session* src = nullptr) {
   int rc;
   *out = nullptr;
   const double t1 = now_ms();
@@ -713,13 +890,24 @@ static int session_from_plan(const HostPlan& H, const RankPlan& R, uint32_t max_
     cudaError_t _e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);                   \
     if (_e != cudaSuccess) { session_free(s); return fail(PPRB200_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(_e)); } \
   } while (0)
-  UP(s->d_row_off, H.row_off.data(), ((size_t)M + 1) * sizeof(long long));
-  if (M) UP(s->d_rowdeg, H.rowdeg.data(), (size_t)M * sizeof(unsigned long long));
-  if (E) UP(s->d_col, H.enc.data(), (size_t)E * sizeof(uint32_t));
-  if (M) UP(s->d_label, H.label.data(), (size_t)M * sizeof(int));
-  if (n) UP(s->d_dense_of, H.dense_of.data(), (size_t)n * sizeof(int));
-  if (n) UP(s->d_pos_of, H.pos_of.data(), (size_t)n * sizeof(int));
-  if (n) UP(s->d_colour, H.colour.data(), (size_t)n);
+#define SHARED(field, host, bytes)                                                                                      \
+  do {                                                                                                                  \
+    if (src) {                                                                                                          \
+      cudaError_t _e = cudaMemcpyPeerAsync(s->field, s->device, src->field, src->device, bytes, st);                    \
+      if (_e != cudaSuccess) { session_free(s); return fail(PPRB200_ERR_CUDA, "peer copy failed: %s", cudaGetErrorString(_e)); } \
+    } else UP(s->field, host, bytes);                                                                                   \
+  } while (0)
+  SHARED(d_row_off, H.row_off.data(), ((size_t)M + 1) * sizeof(long long));
+  if (M) SHARED(d_rowdeg, H.rowdeg.data(), (size_t)M * sizeof(unsigned long long));
+  if (E && !src && H.d_enc) {  // column words made on the device (build_host_plan)
+    cudaError_t _e = cudaMemcpyPeerAsync(s->d_col, s->device, H.d_enc, H.enc_device, (size_t)E * sizeof(uint32_t), st);
+    if (_e != cudaSuccess) { session_free(s); return fail(PPRB200_ERR_CUDA, "device copy of the column words failed: %s", cudaGetErrorString(_e)); }
+  } else if (E) SHARED(d_col, H.enc.data(), (size_t)E * sizeof(uint32_t));
+  if (M) SHARED(d_label, H.label.data(), (size_t)M * sizeof(int));
+  if (n) SHARED(d_dense_of, H.dense_of.data(), (size_t)n * sizeof(int));
+  if (n) SHARED(d_pos_of, H.pos_of.data(), (size_t)n * sizeof(int));
+  if (n) SHARED(d_colour, H.colour.data(), (size_t)n);
+#undef SHARED
   if (world > 1) {
     if ((rc = dev_alloc(&s->d_seq_list, R.seq_list.size()))) { session_free(s); return rc; }
     if (!R.seq_list.empty()) UP(s->d_seq_list, R.seq_list.data(), R.seq_list.size() * sizeof(int));
@@ -830,7 +1018,7 @@ static int session_create_impl(const int64_t* row_ptr, const int32_t* col, int32
   if (rc) return rc;
   if (!plan_out && (rc = device_ok())) return rc;
   HostPlan H;
-  if ((rc = build_host_plan(row_ptr, col, n, colour_in, hub_threshold, world, need_colour, H))) return rc;
+  if ((rc = build_host_plan(row_ptr, col, n, colour_in, hub_threshold, world, need_colour, H, /*use_device=*/plan_out == nullptr))) return rc;
   RankPlan R;
   build_rank_plan(H, rank, R);
   if (plan_out) {
@@ -1620,6 +1808,19 @@ int pprb200_release_cached_memory(void) {
   return PPRB200_OK;
 }
 
+int pprb200_find_partitions_device(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8_t* colour) {
+  int rc = validate_csr(row_ptr, col, n);
+  if (rc) return rc;
+  if (n > 0 && !colour) return fail(PPRB200_ERR_PARAM, "colour is NULL");
+  if ((rc = device_ok())) return rc;
+  if (n == 0) return PPRB200_OK;
+  std::lock_guard<std::mutex> lk(g_api_mutex);
+  RawCsrDev G;
+  if (!G.upload(row_ptr, col, n, row_ptr[n])) return fail(PPRB200_ERR_CUDA, "upload of the graph failed");
+  const ComponentFn on_device = [&](int32_t root, uint8_t* seen, uint8_t* col_out) { return device_component(G, root, seen, col_out); };
+  return find_partitions(row_ptr, col, n, colour, &on_device);
+}
+
 // debug: out[i][4] = Philox4x32-10(counter = ctr_key[i][0..3], key = ctr_key[i][4..5]) computed by the device function of mc_walk.cuh
 int pprb200_debug_philox(const uint32_t* ctr_key, uint32_t* out, int32_t nblocks) {
   if (!ctr_key || !out || nblocks <= 0) return fail(PPRB200_ERR_PARAM, "bad argument");
@@ -1946,7 +2147,7 @@ static int run_oneshot(const int64_t* row_ptr, const int32_t* col, int32_t n, co
   double t_plan = 0, t_up = 0, t_enq = 0, t_run = 0, t_d2h = 0;
   {
     HostPlan H;
-    if ((rc = build_host_plan(row_ptr, col, n, colour, hub_threshold, world, job.mode == MODE_GRANK, H))) return rc;
+    if ((rc = build_host_plan(row_ptr, col, n, colour, hub_threshold, world, job.mode == MODE_GRANK, H, /*use_device=*/true))) return rc;
     t_plan = now_ms();
     if (world > 1) {
       for (int a = 0; a < world && !rc; a++) {
@@ -1968,7 +2169,8 @@ static int run_oneshot(const int64_t* row_ptr, const int32_t* col, int32_t n, co
       if (world > 1) cudaStreamCreateWithFlags(&streams[(size_t)r], cudaStreamNonBlocking);
       RankPlan R;
       build_rank_plan(H, r, R);
-      if ((rc = session_from_plan(H, R, job.L, r, streams[(size_t)r], /*plain cudaMalloc for peer-visible buffers*/ world > 1, &ss[(size_t)r]))) { cleanup(); return rc; }
+      if ((rc = session_from_plan(H, R, job.L, r, streams[(size_t)r], /*plain cudaMalloc for peer-visible buffers*/ world > 1, &ss[(size_t)r],
+                                  r > 0 ? ss[0] : nullptr))) { cleanup(); return rc; }
     }
     t_up = now_ms();
   }

@@ -14,7 +14,10 @@ namespace pprb200 {
 int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
 
 int validate_csr(const int64_t* row_ptr, const int32_t* col, int32_t n);
-int find_partitions(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8_t* colour);
+// device_component (optional): explores the whole component of `root` on the device -- sets seen[v] = 1 and colour[v] =
+// parity of the BFS distance from root for its nodes and returns true, or returns false having touched nothing
+using ComponentFn = std::function<bool(int32_t root, uint8_t* seen, uint8_t* colour)>;
+int find_partitions(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8_t* colour, const ComponentFn* device_component = nullptr);
 
 // ---- host-side parallelism (the front half of a call: colouring, storage order, CSR encode) ----
 // Worker threads are created once per process and reused (PPRB200_HOST_THREADS, default min(hardware threads, 16)).

@@ -80,6 +80,10 @@ int pprb200_device_count(void);
 /* BFS 2-colouring exactly as pprInternal.h:29-99 produces it when the map is iterated in dense order:
  * colour[v] = 0 for partitions.first, 1 for partitions.second. */
 int pprb200_find_partitions(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8_t* colour);
+/* The same colouring the way the session / one-shot entry points compute it on graphs of a million edges and more: the
+ * first non-trivial component (on power-law graphs nearly everything) is levelled by a BFS on the device over the uploaded
+ * CSR (csrc/plan_device.cuh), the rest on the host. Identical output; needs an sm_100 device. */
+int pprb200_find_partitions_device(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8_t* colour);
 
 /* ---- one-shot entry points with HOST buffers (what the template headers call) ---------------------- */
 

@@ -297,3 +297,29 @@ def test_rmat16_full_config_bit_identical_and_properties(hub):
     assert (cnt[sinks] == 1).all() and (ids[sinks, 0] == np.nonzero(sinks)[0]).all() and np.allclose(sc[sinks, 0], 0.15, atol=1e-15)
     srt = np.sort(np.where(valid, ids, np.arange(-50, 0)[None, :]), axis=1)
     assert (np.diff(srt, axis=1) != 0).all()                                    # keys unique inside a basket
+
+
+def test_device_colouring_equals_the_host_colouring():
+    """The session / one-shot entry points level the first non-trivial component with a BFS on the device (plan_device.cuh);
+    the colouring must be the host's (= the reference's FIFO BFS, tests/test_host_logic.py) on every kind of graph."""
+    rng = np.random.default_rng(11)
+    graphs = [G.rmat(12), G.rmat(16), G.rmat(18), G.barabasi_albert(100_000, 4), G.ring(100),
+              G.ring(1000),                                                     # deeper than the byte-sized level counter: host
+              G.from_edges(1, [], []), G.from_edges(5, [], []),                 # isolated nodes only
+              G.from_edges(6, [3, 4], [4, 5]),                                  # nodes 0-2 isolated, the root is node 3
+              G.from_edges(6, [3, 1], [0, 0]),                                  # node 0 is a sink root (in-edges only)
+              G.from_edges(400, rng.integers(0, 200, 900), rng.integers(0, 200, 900)),  # a component + isolated nodes
+              G.from_edges(400, np.r_[rng.integers(0, 200, 900), rng.integers(200, 400, 900)],
+                           np.r_[rng.integers(0, 200, 900), rng.integers(200, 400, 900)])]   # two large components
+    for g in graphs:
+        want = ppr.find_partitions_csr(g)
+        got = ppr.find_partitions_csr(g, device=True)
+        assert (got == want).all(), (g.n, g.n_edges, int((got != want).sum()))
+
+
+def test_one_shot_call_with_the_plan_made_on_the_device_matches_the_oracle():
+    """R-MAT-16 has 2^20 edges: pprb200_grank (colour = NULL) uploads the CSR, colours and encodes on the device"""
+    g = G.rmat(16)
+    got = ppr.grank_csr(g, 50, 100, 6, 0.85, -1.0, hub_threshold=0)
+    want = ob.oracle_grank(g, 50, 100, 6, 0.85, -1.0, hub_threshold=ppr.DEFAULT_HUB_THRESHOLD)
+    assert_bit_identical(got, want, "rmat16 one-shot, device plan")

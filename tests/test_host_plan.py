@@ -106,6 +106,23 @@ def test_host_plan_on_degenerate_graphs():
     check_plan(G.from_edges(500, rng.integers(0, 500, 6000), rng.integers(0, 20, 6000)), 3)  # few targets: in-degree ties
 
 
+def test_host_plan_with_degrees_around_the_counting_sort_cap():
+    """out- and in-degrees at and above 4095 share one counting-sort key and are ordered by a comparison sort afterwards:
+    4094 / 4095 / 4096 / 6000 successors, two hubs with the same degree (tie by id), and targets with in-degree >= 4095"""
+    n = 7000
+    src, dst = [], []
+    for v, d in ((5, 4094), (9, 4095), (2, 4096), (11, 6000), (3, 6000), (40, 4095)):
+        src += [v] * d
+        dst += list(range(100, 100 + d))
+    rng = np.random.default_rng(4)
+    for t, d in ((60, 4095), (61, 4094), (62, 5000), (63, 5000)):   # in-degrees around the cap
+        src += rng.integers(1000, n, d).tolist()
+        dst += [t] * d
+    g = G.from_edges(n, src, dst)
+    for hub in (0, 5000, ppr.NEVER_HUB):
+        check_plan(g, hub)
+
+
 def test_host_plan_shards_partition_the_single_gpu_plan():
     g = G.rmat(12)
     colour = ppr.find_partitions_csr(g)
