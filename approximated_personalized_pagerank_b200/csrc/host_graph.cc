@@ -342,6 +342,66 @@ int find_partitions(const int64_t* row_ptr, const int32_t* col, int32_t n, uint8
     if (timing) fprintf(stderr, "[pprb200] find_partitions: transpose-free bfs %.2f ms (%d host threads)\n", now() - t_begin, T);
     return PPRB200_OK;
   }
+  // Sparse variant: phase A usually leaves isolated nodes and a handful of tiny components. Their in-edges are then a short
+  // list of (target, source) pairs, sorted by target -- no n-sized predecessor arrays, no pass over the seen nodes' edges.
+  if (phase_a && frontier.empty()) {
+    const int parts = (int)std::max<int64_t>(1, std::min<int64_t>(T, ((int64_t)n + (1 << 16) - 1) >> 16));
+    std::vector<std::vector<int32_t>> mine((size_t)parts);
+    std::vector<int64_t> edges_of((size_t)parts, 0);
+    host_parallel(parts, [&](int t) {
+      int64_t cnt = 0;
+      for (int64_t v = std::max<int64_t>(first_root, (int64_t)n * t / parts), hi = (int64_t)n * (t + 1) / parts; v < hi; v++)
+        if (!seen[(size_t)v] && row_ptr[v + 1] > row_ptr[v]) { mine[(size_t)t].push_back((int32_t)v); cnt += row_ptr[v + 1] - row_ptr[v]; }
+      edges_of[(size_t)t] = cnt;
+    });
+    int64_t e_unseen = 0;
+    for (int t = 0; t < parts; t++) e_unseen += edges_of[(size_t)t];
+    if (e_unseen * 8 <= e) {
+      std::vector<std::pair<int32_t, int32_t>> pred;  // (target, source), both unseen
+      pred.reserve((size_t)e_unseen);
+      std::vector<uint8_t> has_pred((size_t)n, 0);
+      for (int t = 0; t < parts; t++)
+        for (const int32_t u : mine[(size_t)t])
+          for (int64_t i = row_ptr[u]; i < row_ptr[u + 1]; i++) { pred.emplace_back(col[i], u); has_pred[(size_t)col[i]] = 1; }
+      std::sort(pred.begin(), pred.end());
+      // isolated nodes are components of their own; what is left are the candidate roots, in ascending id order
+      for (int t = 0; t < parts; t++) mine[(size_t)t].clear();
+      host_parallel(parts, [&](int t) {
+        for (int64_t v = std::max<int64_t>(first_root, (int64_t)n * t / parts), hi = (int64_t)n * (t + 1) / parts; v < hi; v++)
+          if (!seen[(size_t)v]) {
+            if (row_ptr[v + 1] == row_ptr[v] && !has_pred[(size_t)v]) { seen[(size_t)v] = 1; colour[v] = 0; }
+            else mine[(size_t)t].push_back((int32_t)v);
+          }
+      });
+      for (int t = 0; t < parts; t++)
+        for (const int32_t root : mine[(size_t)t]) {
+          if (seen[(size_t)root]) continue;
+          seen[(size_t)root] = 1;
+          colour[root] = 0;
+          frontier.assign(1, root);
+          other = 1;
+          while (!frontier.empty()) {
+            next.clear();
+            for (const int32_t x : frontier) {
+              for (int64_t i = row_ptr[x]; i < row_ptr[x + 1]; i++) {
+                const int32_t sx = col[i];
+                if (!seen[(size_t)sx]) { seen[(size_t)sx] = 1; colour[sx] = other; next.push_back(sx); }
+              }
+              for (auto it = std::lower_bound(pred.begin(), pred.end(), std::make_pair(x, (int32_t)0)); it != pred.end() && it->first == x; ++it) {
+                const int32_t px = it->second;
+                if (!seen[(size_t)px]) { seen[(size_t)px] = 1; colour[px] = other; next.push_back(px); }
+              }
+            }
+            frontier.swap(next);
+            other ^= 1u;
+          }
+        }
+      if (timing)
+        fprintf(stderr, "[pprb200] find_partitions: first component %.2f ms, %lld edges among the rest: sparse bfs %.2f ms (%d host threads)\n",
+                t_a - t_begin, (long long)e_unseen, now() - t_a, T);
+      return PPRB200_OK;
+    }
+  }
   std::vector<int64_t> prow;
   std::vector<int32_t> pcol;
   host_transpose(row_ptr, col, n, prow, pcol, phase_a ? seen.data() : nullptr);

@@ -77,6 +77,8 @@ struct DenseParams {
   int work_idx;
   unsigned int* fb_queue;       // items handed to merge_par_kernel
   int fb_idx;                   // its length: st->qcount[fb_idx]
+  int min_old;                  // nodes whose old basket holds fewer entries than this are handed over unread (L: only full baskets stay)
+  int tail_limit;               // distinct tail labels the table admits (<= the instantiation's TLIMIT; tests lower it to force the rounds)
   unsigned long long* prof;     // optional [gridDim.x * 8] phase cycle counters (PPRB200_PROF=1)
   // hub teams (below): work indices [0, n_team_items) are chunks of team hubs, the rest the items above
   const int* team_item_pos;
@@ -159,6 +161,7 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
   const int write_slot = st->slot[M.colour] ^ 1;
   unsigned long long s_merged = 0, s_edges = 0, s_cands = 0, s_truncs = 0, s_ties = 0, s_bytes = 0, s_nodes = 0, s_requeue = 0;
 
+  const int tlimit = P.tail_limit > 0 && P.tail_limit < TLIMIT ? P.tail_limit : TLIMIT;
   auto home_of = [](unsigned int hk) -> unsigned int { return hk & (unsigned)(TCAP - 1); };
   auto bucket_of = [](unsigned int hk) -> unsigned int { return hk >> (32 - RBITS); };
   // exact accumulate of a tail label (pass 2); false when the key is absent and the table is closed
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
       const int cur = keys[h];
       if (cur == k) break;
       if (cur == KEY_EMPTY) {
-        if (*reinterpret_cast<volatile int*>(&S->tcount) >= TLIMIT) return false;
+        if (*reinterpret_cast<volatile int*>(&S->tcount) >= tlimit) return false;
         const int old = atomicCAS(&t_keys[h], KEY_EMPTY, k);
         if (old == KEY_EMPTY) { const int pos = atomicAdd(&S->tcount, 1); t_list[pos] = (unsigned short)h; break; }
         if (old == k) break;
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
     // the work item handed to merge_par_kernel when this node cannot be finished here (a team: its undivided item)
     const unsigned int handover_item = team >= 0 ? (unsigned int)P.teams[team].regular_item : (unsigned int)P.item_base + ritem;
     if (team < 0 && deg > (long long)P.chunk) {  // a chunk of a hub split for merge_par_kernel: the general kernel's job
-      if (tid == 0) { P.fb_queue[atomicAdd(&st->qcount[P.fb_idx], 1u)] = handover_item; dbg[6]++; }
+      if (tid == 0) P.fb_queue[atomicAdd(&st->qcount[P.fb_idx], 1u)] = handover_item;
       continue;
     }
     const int self_id = M.g.label[p];
@@ -294,7 +297,8 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
         }
       }
       block_reduce_min_sum(mn, cntv, S->red_a);
-      if (cntv >= L) theta0 = __longlong_as_double((long long)mn);
+      // (a basket that is not full yet still gives a first guess: the level counts below validate whatever is used)
+      if (cntv >= (long long)P.min_old) theta0 = __longlong_as_double((long long)mn);
     }
     const int npre = S->tcount;  // (block_reduce_min_sum ends with a barrier)
     if (theta0 == 0.0) {
@@ -558,6 +562,7 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
     // bound of the cut (0 when none is); scan 2 compacts the candidates >= tau.
     bool dropped_local = false;  // this thread saw a candidate that is not in the compact arrays
     bool wide = false;           // more candidates than the compact arrays hold: select / write address the tables themselves
+    bool rounds_used = false;    // pass 2 ran slice by slice: its labels live in the compact arrays only
     double tau = 0.0;
     int n = 0;
     if (!bail) {
@@ -585,6 +590,25 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
         }
         __syncthreads();
         tau = DS->lvl[0] >= L ? theta0 : (DS->lvl[1] >= L ? theta0 * 0.75 : (DS->lvl[2] >= L ? theta0 * 0.5 : (DS->lvl[3] >= L ? theta0 * 0.0625 : 0.0)));
+      }
+      if (tau == 0.0 && team < 0) {
+        // No guess held -- a basket in its first sweeps, whose old content says little about the new cut. The L-th largest
+        // EXACT candidate bounds the cut from below just as well (L labels reach it), at the price of one more select:
+        // without it every non-empty bucket survives, and these nodes overflow the tail table or the candidate arrays.
+        long long nz = 0;
+        for (int i = tid; i < H; i += THREADS) { const uint2 a = acc[i]; nz += (a.x | a.y) != 0u; }
+        for (int i = tid; i < npre; i += THREADS) { const uint2 a = t_acc[t_list[i]]; nz += (a.x | a.y) != 0u; }
+        nz = block_reduce_sum_ll(nz, S->red_a);
+        if (nz > (long long)L) {
+          auto xbits = [&](int i) -> unsigned long long {
+            const uint2 a = i < H ? acc[i] : t_acc[t_list[i - H]];
+            return (unsigned long long)__double_as_longlong(word_score(a));
+          };
+          auto xok = [&](int i) -> bool { const uint2 a = i < H ? acc[i] : t_acc[t_list[i - H]]; return (a.x | a.y) != 0u; };
+          bool tie1;
+          int krem1;
+          tau = __longlong_as_double((long long)block_radix_select(H + npre, L, xbits, xok, S, &tie1, &krem1));
+        }
       }
       const unsigned long long tb0 = (unsigned long long)__double_as_longlong(tau);
       const long long floor_tau = (long long)(tau * scale) - 2048;
@@ -648,8 +672,6 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
       any = __syncthreads_or(any);
       DPROF_MARK(3);
       dbg[1] += any != 0;
-      if (any && clen > 1024) dbg[6]++;   // (profiling: pass 2 on a hub)
-      if (clen > 1024) dbg[3]++;          // (profiling: hubs seen)
       if (team >= 0) {  // (finishing member) tell the team: done, or pass 2 with this alive bitmap
         if (any) {
           for (int i = tid; i < R / 32; i += THREADS) g_alive[i] = s_alive[i];
@@ -659,27 +681,86 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
         if (tid == 0) { __threadfence(); *reinterpret_cast<volatile unsigned int*>(&hdr->decision) = any ? 2u : 1u; }
       }
       if (any) {
-        // (the node's own label is normally a pre label; if it lost its home slot its self term went to the sketch too)
-        if (tid == 0 && wanted(self_id) && !tail_add(self_id, xself)) S->spilled = 1;
-        sweep(2);
-        __syncthreads();
-        if (team >= 0) {
-          // the other members' exact (label, sum) pairs: wait for all of them, then fold them into this table
-          if (tid == 0) {
-            while (*reinterpret_cast<volatile unsigned int*>(&hdr->done2) < (unsigned)team_n - 1u) __nanosleep(100);
-            __threadfence();
-            DS->team_base = *reinterpret_cast<volatile unsigned int*>(&hdr->tail_count);
-            if (*reinterpret_cast<volatile unsigned int*>(&hdr->bad) & 2u) S->spilled = 1;
+        // Pass 2, and its second chance. More surviving tail labels than the table admits (hubs of a few thousand successors,
+        // ~600 per iteration on R-MAT-22) used to send the node to merge_par_kernel: three full passes on the slow path, and
+        // the critical path of a multi-GPU iteration. Instead the sweep is repeated in PASS2_ROUNDS rounds, each over the
+        // buckets of one slice of the hash range: a round's labels are summed exactly, those that reach the bound move to the
+        // compact candidate arrays, and the table is emptied for the next slice.
+        constexpr int PASS2_ROUNDS = 4, ROUND_SHIFT = RBITS - 2;
+        int nrounds = 1;
+        for (int attempt = 0;; attempt++) {
+          for (int r = 0; r < nrounds; r++) {
+            if (nrounds > 1) {
+              for (int i0 = 0; i0 < R; i0 += THREADS) {  // this round's slice of the alive bitmap
+                const int i = i0 + tid;
+                const bool al = i < R && sk[i] >= sk_floor && (i >> ROUND_SHIFT) == r;
+                const unsigned m = __ballot_sync(FULL, al);
+                if (lane == 0 && i < R) s_alive[i >> 5] = m;
+              }
+              __syncthreads();
+            }
+            // (the node's own label is normally a pre label; if it lost its home slot its self term went to the sketch too)
+            if (tid == 0 && wanted(self_id) && !tail_add(self_id, xself)) S->spilled = 1;
+            sweep(2);
+            __syncthreads();
+            if (team >= 0) {
+              // the other members' exact (label, sum) pairs: wait for all of them, then fold them into this table
+              if (tid == 0) {
+                while (*reinterpret_cast<volatile unsigned int*>(&hdr->done2) < (unsigned)team_n - 1u) __nanosleep(100);
+                __threadfence();
+                DS->team_base = *reinterpret_cast<volatile unsigned int*>(&hdr->tail_count);
+                if (*reinterpret_cast<volatile unsigned int*>(&hdr->bad) & 2u) S->spilled = 1;
+              }
+              __syncthreads();
+              const unsigned int npairs = DS->team_base;
+              for (unsigned int i = tid; i < npairs; i += THREADS) {
+                if (!tail_add(__ldcg(&g_tail[i].key), __ldcg(&g_tail[i].acc))) S->spilled = 1;
+              }
+              __syncthreads();
+            }
+            if (S->spilled) break;
+            if (nrounds > 1) {
+              const int nt0 = S->tcount;
+              for (int i0 = npre; i0 < nt0; i0 += THREADS) {  // this round's labels: candidates that reach the bound, then out
+                const int i = i0 + tid;
+                bool ok = i < nt0;
+                unsigned long long bits = 0ull;
+                int id = 0;
+                if (ok) {
+                  const int sl = t_list[i];
+                  id = t_keys[sl];
+                  bits = (unsigned long long)__double_as_longlong(word_score(t_acc[sl]));
+                  ok = bits >= thb;
+                  dropped_local |= !ok;
+                  t_keys[sl] = KEY_EMPTY;
+                  t_acc[sl] = make_uint2(0u, 0u);
+                }
+                append(ok, bits, id);
+              }
+              __syncthreads();
+              if (tid == 0) S->tcount = npre;
+              __syncthreads();
+            }
+          }
+          if (!S->spilled || attempt == 1 || team >= 0 || wide) break;
+          dbg[5]++;
+          // second chance: drop what the first attempt put into the table and go round by round
+          {
+            const int nt0 = S->tcount;
+            for (int i = npre + tid; i < nt0; i += THREADS) {
+              const int sl = t_list[i];
+              t_keys[sl] = KEY_EMPTY;
+              t_acc[sl] = make_uint2(0u, 0u);
+            }
           }
           __syncthreads();
-          const unsigned int npairs = DS->team_base;
-          for (unsigned int i = tid; i < npairs; i += THREADS) {
-            if (!tail_add(__ldcg(&g_tail[i].key), __ldcg(&g_tail[i].acc))) S->spilled = 1;
-          }
+          if (tid == 0) { S->tcount = npre; S->spilled = 0; }
           __syncthreads();
+          nrounds = PASS2_ROUNDS;
         }
-        if (S->spilled) { bail = true; dbg[5]++; }
-        if (!bail) {
+        rounds_used = nrounds > 1;
+        if (S->spilled) { bail = true; if (!rounds_used) dbg[5]++; }
+        if (!bail && !rounds_used) {
           const int nt0 = S->tcount;
           for (int i0 = npre; i0 < nt0; i0 += THREADS) {
             const int i = i0 + tid;
@@ -698,6 +779,10 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
           __syncthreads();
           n = S->ncand;
           if (n > CMAX && !wide) { wide = true; dbg[4]++; }
+        } else if (!bail) {
+          n = S->ncand;
+          if (n > CMAX) bail = true;  // (the round's labels left the table: no wide select from it)
+          else dbg[6]++;
         }
       }
       DPROF_MARK(4);
@@ -822,7 +907,11 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
                   if (cur == KEY_EMPTY) break;
                 }
               }
-              const double nv_ = word_score(a);
+              double nv_ = word_score(a);
+              if (!found && rounds_used && ids[e] >= H) {  // (an old label without a home slot: among the rounds' candidates, or below the cut)
+                for (int j = 0; j < n; j++)
+                  if (c_id[j] == ids[e]) { nv_ = __longlong_as_double((long long)c_bits[j]); found = true; break; }
+              }
               const bool in_new = found && selected((unsigned long long)__double_as_longlong(nv_), ids[e]);
               if (in_new) dsum += fix_norm(fabs(nv_ - xs[e])) - fix_norm(nv_);
               else dsum += fix_norm(xs[e]);
@@ -856,7 +945,7 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
     }
     if (bail) {
       // partial sums dropped; merge_par_kernel runs the node from scratch (same sums, global table)
-      if (tid == 0) { P.fb_queue[atomicAdd(&st->qcount[P.fb_idx], 1u)] = handover_item; s_requeue++; }
+      if (tid == 0) { P.fb_queue[atomicAdd(&st->qcount[P.fb_idx], 1u)] = handover_item; s_requeue++; dbg[3] += (unsigned long long)clen; }
     } else {
       unsigned long long mg = (unsigned long long)block_reduce_sum_ll((long long)merged, S->red_a);
       if (tid == 0) {

@@ -1258,6 +1258,15 @@ static int enqueue_par(pprb200_session* s, const MergeParams& M, int c, int L) {
       D.work_idx = 8 + cls;
       D.fb_queue = s->d_fb_queue;
       D.fb_idx = 4;
+      {
+        // (1: every node with an old basket at all stays on merge_dense_kernel -- the exact-candidate bound covers baskets
+        // that are not full yet, R-MAT-22 job 1 844 -> 1 781 ms; PPRB200_MIN_OLD=0 restores the hand-over of not-full baskets)
+        const char* mo = getenv("PPRB200_MIN_OLD");
+        const int min_old_env = mo ? atoi(mo) : 1;
+        D.min_old = min_old_env >= 1 ? std::min(min_old_env, L) : L;
+        const char* tl = getenv("PPRB200_TAIL_LIMIT");  // tests: force the pass-2 rounds on small graphs
+        D.tail_limit = tl ? atoi(tl) : 0;
+      }
       D.prof = s->d_prof ? s->d_prof + (size_t)cls * s->sm_count * 8 * 8 : nullptr;
       s->cur = cls == 0 ? side : s->stream;
       cudaError_t err;

@@ -121,6 +121,46 @@ def test_hub_teams_give_the_same_bits_as_single_owner_ctas(monkeypatch, scale, t
     assert_bit_identical(got, solo, "teams vs single-owner CTAs")
 
 
+@pytest.mark.parametrize("limit", [8, 40])
+def test_tail_table_overflow_is_finished_in_rounds_not_handed_over(monkeypatch, limit):
+    """More surviving tail labels than the tail table admits (here: the table artificially closed after a few labels; on
+    R-MAT-22 some 600 hubs per iteration do it by themselves): merge_dense_kernel repeats pass 2 slice by slice over the hash
+    range, its labels moving to the compact candidate arrays round by round, instead of sending the node to
+    merge_par_kernel. Same bits as the oracle, and the bookkeeping counters show that the path was taken."""
+    import ctypes as C
+    from approximated_personalized_pagerank_b200 import _lib
+    monkeypatch.setenv("PPRB200_TAIL_LIMIT", str(limit))
+    g = G.rmat(14)
+    colour = ppr.find_partitions_csr(g)
+    s = ppr.Session(g, 100, colour=colour, hub_threshold=0)
+    try:
+        s.grank(50, 100, 8, 0.85, -1.0)
+        got = s.fetch()
+        got.stats = s.stats()
+        d = (C.c_ulonglong * 8)()
+        _lib.load().pprb200_debug_counters(s.handle, d)
+    finally:
+        s.close()
+    want = ob.oracle_grank(g, 50, 100, 8, 0.85, -1.0, colour=colour, hub_threshold=ppr.DEFAULT_HUB_THRESHOLD)
+    assert_bit_identical(got, want, f"pass-2 rounds, tail limit {limit}")
+    for k in HUB_STAT_KEYS:
+        assert got.stats[k] == want.stats[k], (k, got.stats[k], want.stats[k])
+    assert d[5] > 0 and d[6] > 0, list(d)   # tail table full, and finished in rounds
+
+
+def test_not_full_baskets_stay_on_the_dense_kernel_or_are_handed_over_same_bits(monkeypatch):
+    """first sweeps: the old basket is not full and bounds nothing; the L-th largest exact candidate does (default), or the
+    node goes to merge_par_kernel unread (PPRB200_MIN_OLD=0, round 2's first scheme)"""
+    g = G.rmat(13)
+    res = []
+    for mo in ("1", "0", "30"):
+        monkeypatch.setenv("PPRB200_MIN_OLD", mo)
+        got, want = run_pair(g, 50, 100, 5, 0.85, -1.0, hub=12)
+        assert_bit_identical(got, want, f"min_old {mo}")
+        res.append(got.stats["overflow_requeues"])
+    assert res[0] <= res[2] <= res[1] and res[0] < res[1], res
+
+
 def test_two_pass_sketch_path_on_a_large_graph():
     """graphs with more than 16 x 8192 nodes take the sketch-filtered two-pass merge for single-item hubs"""
     g = G.rmat(18)

@@ -16,4 +16,4 @@ for r in range(reps):
     if os.environ.get('PPRB200_COUNTERS'):
         d = (C.c_ulonglong * 8)()
         _lib.load().pprb200_debug_counters(s.handle, d)
-        print("  dense: nodes %d pass2 %d tau0 %d hubs %d wide %d tailfull %d hubs-pass2 %d oldnotfull %d" % tuple(d[i] for i in range(8)))
+        print("  dense: nodes %d pass2 %d tau0 %d successors-handed-over-after-reading %d wide %d tailfull %d finished-in-rounds %d oldnotfull %d" % tuple(d[i] for i in range(8)))
