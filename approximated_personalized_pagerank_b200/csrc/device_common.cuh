@@ -73,18 +73,37 @@ struct PeerDev {
   unsigned char* buf[MAX_WORLD][2];  // peer basket buffers (entry [rank] = the local ones)
   Mailbox* mbox[MAX_WORLD];          // peer mailboxes: mbox[r][parity * MAX_WORLD + sender]
   long long timeout_cycles;          // a barrier gives up after this many SM clocks (default ~30 s; PPRB200_PEER_TIMEOUT_MS)
+  int push_mode;                     // A/B hook (PPRB200_PUSH_MODE): 0 = every 16 bytes to all peers in turn, 1 = peer by peer,
+                                     // 2 = nothing is pushed (WRONG results: timing experiments only), 3 = to every peer (no need masks)
+  const unsigned char* need;         // [M] bit r: rank r owns a predecessor of the node at this position, i.e. reads its basket
+                                     // during the iterations (nullptr: everybody gets everything)
 };
 
 // copy the freshly written slot of position p to every peer; `lane`/`nlanes` = the calling warp or CTA.
 // The caller must have made the local slot visible to all calling threads (__syncwarp / __syncthreads).
-__device__ __forceinline__ void publish_slot(const PeerDev& pd, int which_buf, size_t slot_off, size_t bytes, int lane, int nlanes) {
+// Only peers that READ the basket get it (pd.need): on 8 GPUs a node of in-degree 4 has its predecessors on ~3 of them, and
+// pushing to all 7 made the NVLink stores the bottleneck of an iteration (profiles/r2/sweeps.txt); whoever was left out
+// receives the final baskets once, after the last iteration (final_push_kernel).
+__device__ __forceinline__ void publish_slot(const PeerDev& pd, int which_buf, size_t slot_off, size_t bytes, int lane, int nlanes, int p) {
   if (pd.world <= 1) return;
   const int4* src = reinterpret_cast<const int4*>(pd.buf[pd.rank][which_buf] + slot_off);
   const int n16 = (int)(bytes >> 4);
+  if (pd.push_mode == 2) return;
+  unsigned int mask = (pd.need && pd.push_mode != 3 && p >= 0) ? (unsigned int)pd.need[p] : 0xffu;  // (p < 0: to everybody)
+  mask &= ~(1u << pd.rank) & ((1u << pd.world) - 1u);
+  if (mask == 0u) return;
+  if (pd.push_mode == 1) {
+    for (int r = 0; r < pd.world; r++) {
+      if (!((mask >> r) & 1u)) continue;
+      int4* dst = reinterpret_cast<int4*>(pd.buf[r][which_buf] + slot_off);
+      for (int i = lane; i < n16; i += nlanes) __stcg(dst + i, __ldcg(src + i));
+    }
+    return;
+  }
   for (int i = lane; i < n16; i += nlanes) {
     const int4 v = __ldcg(src + i);
     for (int r = 0; r < pd.world; r++)
-      if (r != pd.rank) __stcg(reinterpret_cast<int4*>(pd.buf[r][which_buf] + slot_off) + i, v);
+      if ((mask >> r) & 1u) __stcg(reinterpret_cast<int4*>(pd.buf[r][which_buf] + slot_off) + i, v);
   }
 }
 

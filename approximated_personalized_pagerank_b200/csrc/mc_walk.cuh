@@ -316,7 +316,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : 3)) mc_walk_ker
     __syncthreads();
     // leave the table empty for the next source
     for (int i = tid; i < n; i += THREADS) { const unsigned int h = slot_at(i); tbl[h].key = WALK_EMPTY; tbl[h].count = 0u; }
-    publish_slot(P.peers, write_slot, (size_t)p * slot_bytes(Lp), slot_bytes(Lp), tid, THREADS);
+    // (to every peer, whatever the need masks say: walk sources are dealt out round-robin, not to the ranks that own the
+    // positions in the combine rounds -- the owner reads this basket as its old one, and with rounds = 0 it is the result)
+    publish_slot(P.peers, write_slot, (size_t)p * slot_bytes(Lp), slot_bytes(Lp), tid, THREADS, -1);
     steps = (unsigned long long)block_reduce_sum_ll((long long)steps, S->P.red_a);
     if (tid == 0) {
       tot_steps += steps;

@@ -924,7 +924,7 @@ __global__ void __launch_bounds__(THREADS, MINB) merge_dense_kernel(DenseParams 
         if (tid == 0 && dsum > 0) atomicMax(&st->cur_max, dsum);
       }
       __syncthreads();
-      publish_slot(M.peers, write_slot, (size_t)p * slotb, slotb, tid, THREADS);
+      publish_slot(M.peers, write_slot, (size_t)p * slotb, slotb, tid, THREADS, p);
     }
     DPROF_MARK(6);
     // ---- leave the tables clean ----

@@ -1052,7 +1052,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 3 : 1)) merge_par_k
         if (tid == 0 && dsum > 0) atomicMax(&st->cur_max, dsum);
       }
       __syncthreads();
-      publish_slot(M.peers, write_slot, (size_t)p * slot_bytes(Lp), slot_bytes(Lp), tid, THREADS);
+      publish_slot(M.peers, write_slot, (size_t)p * slot_bytes(Lp), slot_bytes(Lp), tid, THREADS, p);
       if (use_global) {
         // leave the pool table clean and hand it back
         for (int i = tid; i < n; i += THREADS) {

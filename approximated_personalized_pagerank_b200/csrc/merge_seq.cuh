@@ -333,7 +333,7 @@ __device__ bool merge_node_seq(const MergeParams& P, const WarpTable<IdxT>& T, u
     if (dsum > warp_maxdiff) warp_maxdiff = dsum;
   }
   __syncwarp();
-  publish_slot(P.peers, write_slot, (size_t)p * slot_bytes(Lp), slot_bytes(Lp), lane, 32);
+  publish_slot(P.peers, write_slot, (size_t)p * slot_bytes(Lp), slot_bytes(Lp), lane, 32, p);
   // reset the table through the occupied-slot list
   for (int i = lane; i < n; i += 32) T.keys[T.list[i]] = KEY_EMPTY;
   if (lane == 0) {

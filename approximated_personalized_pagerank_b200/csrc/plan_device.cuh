@@ -57,4 +57,22 @@ __global__ void __launch_bounds__(256) encode_kernel(const long long* __restrict
   }
 }
 
+// need[q] |= 1 << owner[p] for every stored successor q of position p: the ranks that read q's basket (multi-GPU pushes)
+__global__ void __launch_bounds__(256) need_mask_kernel(const long long* __restrict__ row_off, const unsigned int* __restrict__ enc,
+                                                         const unsigned char* __restrict__ owner, int M, unsigned int* need32) {
+  const int lane = threadIdx.x & 31;
+  const long long stride = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < M; p += stride) {
+    const unsigned int bit = 1u << owner[p];
+    const long long rb = row_off[p], re = row_off[p + 1];
+    for (long long i = rb + lane; i < re; i += 32) {
+      const unsigned int w = enc[i];
+      if (w & 0x80000000u) continue;  // a sink: no basket
+      const unsigned int q = w & 0x3fffffffu;
+      const unsigned int m = bit << ((q & 3u) * 8u);
+      if (!(need32[q >> 2] & m)) atomicOr(&need32[q >> 2], m);
+    }
+  }
+}
+
 }  // namespace pprb200

@@ -84,6 +84,29 @@ __global__ void phase_end_kernel(RunState* st, int clear_stats, int flip_both, P
   }
 }
 
+// Multi-GPU, after the last iteration: during the run a basket only went to the ranks that read it (PeerDev::need); now
+// every rank that was left out receives the final one, so that each rank holds the complete result for its final top-K.
+// One warp per position this rank owns.
+__global__ void __launch_bounds__(256) final_push_kernel(const RunState* st, PeerDev pd, const unsigned char* owner, int M, int pos_split, int Lp) {
+  const int lane = threadIdx.x & 31;
+  const long long stride = ((long long)gridDim.x * blockDim.x) >> 5;
+  const size_t sb = slot_bytes(Lp);
+  const int n16 = (int)(sb >> 4);
+  const unsigned int all = (1u << pd.world) - 1u;
+  for (long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < M; p += stride) {
+    if (owner[p] != (unsigned char)pd.rank) continue;
+    const unsigned int missing = all & ~((unsigned int)pd.need[p] | (1u << pd.rank));
+    if (!missing) continue;
+    const int b = st->slot[p >= pos_split ? 1 : 0];
+    const int4* src = reinterpret_cast<const int4*>(pd.buf[pd.rank][b] + (size_t)p * sb);
+    for (int i = lane; i < n16; i += 32) {
+      const int4 v = __ldcg(src + i);
+      for (int r = 0; r < pd.world; r++)
+        if ((missing >> r) & 1u) __stcg(reinterpret_cast<int4*>(pd.buf[r][b] + (size_t)p * sb) + i, v);
+    }
+  }
+}
+
 // end of GRank iteration `it` (0-based) on `colour`: grank.h:129-140 + the loop test of :92
 __global__ void iter_end_kernel(RunState* st, int colour, double tolerance, PeerDev peers) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -197,6 +220,9 @@ struct pprb200_session {
   bool ipc = false;                 // basket buffers / mailbox are plain cudaMalloc allocations (exported through CUDA IPC)
   PeerDev peers;                    // device view of the peer mappings (world 1: zeroed)
   int* d_seq_list = nullptr;        // world > 1: own positions of the exact-order class (range_begin/end index it)
+  unsigned char* d_need = nullptr;  // world > 1, [M]: ranks that read the basket at a position (PeerDev::need)
+  unsigned char* d_owner = nullptr; // world > 1, [M]: rank that owns the position
+  int pos_split = 0;                // first position of colour 1
   Mailbox* d_mbox = nullptr;        // [2][MAX_WORLD] barrier mailboxes of this rank, written by the peers
   void* ipc_opened[MAX_WORLD][3];   // peer mappings to close
   bool attached = false;
@@ -345,7 +371,7 @@ static void session_free(pprb200_session* s) {
   const bool ipc = s->ipc;
   dev_free(s->d_mbox, ipc);
   dev_free(s->d_buf[0], ipc); dev_free(s->d_buf[1], ipc);
-  void* plain[] = {s->d_rowdeg, s->d_seq_list, s->d_row_off, s->d_col, s->d_label, s->d_pos_of, s->d_dense_of, s->d_colour, s->d_queue[0], s->d_queue[1],
+  void* plain[] = {s->d_need, s->d_owner, s->d_rowdeg, s->d_seq_list, s->d_row_off, s->d_col, s->d_label, s->d_pos_of, s->d_dense_of, s->d_colour, s->d_queue[0], s->d_queue[1],
                    s->d_queue[2], s->d_queue[3], s->d_ncand, s->d_state, s->d_final_stats, s->d_ws, s->d_out_ids, s->d_out_scores,
                    s->d_out_cnt, s->d_item_pos, s->d_item_off, s->d_item_len, s->d_pool, s->d_walk_ws, s->d_prof, s->d_tbl_inuse,
                    s->d_tbl_count, s->d_node_tbl, s->d_node_done, s->d_fb_queue, s->d_team_item_pos, s->d_team_item_off,
@@ -504,6 +530,7 @@ struct HostPlan {
   std::vector<int32_t> order, owner_of_pos, dense_of, rank_of, pos_of, label;
   std::vector<long long> row_off;
   std::vector<unsigned long long> rowdeg;
+  std::vector<uint8_t> owner8, need_mask;  // world > 1, per position: owning rank; ranks that read the basket (bit r: rank r owns a predecessor)
   std::vector<uint32_t> enc;     // column words in storage order -- on the host (small graphs, pprb200_debug_host_plan) ...
   uint32_t* d_enc = nullptr;     // ... or produced on the device (plan_device.cuh): then `enc` stays empty
   int enc_device = 0;
@@ -742,6 +769,25 @@ static int build_host_plan(const int64_t* row_ptr, const int32_t* col, int32_t n
         cudaMemcpyAsync(d_word, word_of.data(), (size_t)n * sizeof(unsigned int), cudaMemcpyHostToDevice, 0) == cudaSuccess) {
       encode_kernel<<<sm * 8, 256, 0, 0>>>(G.row_ptr, G.col, d_order, d_off, d_word, M, H.d_enc);
       encoded = cudaGetLastError() == cudaSuccess && cudaStreamSynchronize(0) == cudaSuccess;
+      if (encoded && world > 1) {  // who reads whose basket (publish_slot)
+        unsigned char* d_owner = nullptr;
+        unsigned int* d_need = nullptr;
+        const size_t words = ((size_t)M + 3) / 4;
+        H.owner8.resize((size_t)M);
+        for (int32_t p2 = 0; p2 < M; p2++) H.owner8[(size_t)p2] = (uint8_t)H.owner_of_pos[(size_t)p2];
+        H.need_mask.assign(words * 4, 0);
+        bool ok = cudaMallocAsync((void**)&d_owner, (size_t)M, 0) == cudaSuccess && cudaMallocAsync((void**)&d_need, words * 4, 0) == cudaSuccess &&
+                  cudaMemcpyAsync(d_owner, H.owner8.data(), (size_t)M, cudaMemcpyHostToDevice, 0) == cudaSuccess &&
+                  cudaMemsetAsync(d_need, 0, words * 4, 0) == cudaSuccess;
+        if (ok) {
+          need_mask_kernel<<<sm * 8, 256, 0, 0>>>(d_off, H.d_enc, d_owner, M, d_need);
+          ok = cudaMemcpyAsync(H.need_mask.data(), d_need, words * 4, cudaMemcpyDeviceToHost, 0) == cudaSuccess && cudaStreamSynchronize(0) == cudaSuccess;
+        }
+        cudaGetLastError();
+        if (d_owner) cudaFreeAsync(d_owner, 0);
+        if (d_need) cudaFreeAsync(d_need, 0);
+        if (!ok) H.need_mask.clear();  // (computed on the host below)
+      }
     }
     cudaGetLastError();
     if (d_order) cudaFreeAsync(d_order, 0);
@@ -762,6 +808,22 @@ static int build_host_plan(const int64_t* row_ptr, const int32_t* col, int32_t n
         for (int64_t i = row_ptr[v]; i < row_ptr[v + 1]; i++) H.enc[(size_t)o++] = word_of[(size_t)col[i]];
       }
     });
+  }
+  if (world > 1 && M > 0 && H.need_mask.empty()) {
+    H.owner8.resize((size_t)M);
+    for (int32_t p2 = 0; p2 < M; p2++) H.owner8[(size_t)p2] = (uint8_t)H.owner_of_pos[(size_t)p2];
+    if (!H.enc.empty()) {
+      H.need_mask.assign(((size_t)M + 3) / 4 * 4, 0);
+      host_parallel_for(M, 1 << 14, [&](int, int64_t lo, int64_t hi) {
+        for (int64_t p2 = lo; p2 < hi; p2++) {
+          const uint8_t bit = (uint8_t)(1u << H.owner8[(size_t)p2]);
+          for (long long i = H.row_off[(size_t)p2]; i < H.row_off[(size_t)p2 + 1]; i++) {
+            const uint32_t w = H.enc[(size_t)i];
+            if (!(w & COL_SINK) && !(H.need_mask[w & COL_POS_MASK] & bit)) __atomic_fetch_or(&H.need_mask[w & COL_POS_MASK], bit, __ATOMIC_RELAXED);
+          }
+        }
+      });
+    }  // (else: the column words exist on the device only and the mask kernel failed -- everybody gets everything)
   }
   H.prep_ms = now_ms() - t0;
   if (getenv("PPRB200_HOST_TIMING"))
@@ -908,9 +970,15 @@ static int session_from_plan(const HostPlan& H, const RankPlan& R, uint32_t max_
   if (n) SHARED(d_pos_of, H.pos_of.data(), (size_t)n * sizeof(int));
   if (n) SHARED(d_colour, H.colour.data(), (size_t)n);
 #undef SHARED
+  s->pos_split = H.cls_begin[1][0];
   if (world > 1) {
     if ((rc = dev_alloc(&s->d_seq_list, R.seq_list.size()))) { session_free(s); return rc; }
     if (!R.seq_list.empty()) UP(s->d_seq_list, R.seq_list.data(), R.seq_list.size() * sizeof(int));
+    if (M > 0 && !H.need_mask.empty() && !getenv("PPRB200_NO_NEED_MASK")) {
+      if ((rc = dev_alloc(&s->d_need, H.need_mask.size())) || (rc = dev_alloc(&s->d_owner, (size_t)M))) { session_free(s); return rc; }
+      UP(s->d_need, H.need_mask.data(), H.need_mask.size());
+      UP(s->d_owner, H.owner8.data(), (size_t)M);
+    }
   }
   if (s->n_items > 0) {
     // global-table pool of the order-free path: one table per CTA that can be in flight, sized for the worst case of
@@ -1353,6 +1421,12 @@ static int ensure_outputs(pprb200_session* s, uint32_t K) {
 }
 
 static int enqueue_final(pprb200_session* s, int L, uint32_t K, double sink_score) {
+  if (s->world > 1 && s->peers.need && s->peers.push_mode != 3 && s->M > 0) {
+    // complete every rank's copy of the result (see final_push_kernel), then wait until everybody's pushes have landed
+    final_push_kernel<<<s->sm_count * 8, 256, 0, s->stream>>>(s->d_state, s->peers, s->d_owner, s->M, s->pos_split, roundup4(L));
+    phase_end_kernel<<<1, 1, 0, s->stream>>>(s->d_state, 0, 0, s->peers, 1);
+    s->launch_count += 2;
+  }
   const int Lp = roundup4(L);
   const int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(200 * 1024) / ((size_t)Lp * 12)));
   const size_t smem = (size_t)warps * Lp * 12;
@@ -1691,7 +1765,8 @@ static void preload(F* kernel) {
   cudaFuncGetAttributes(&attr, reinterpret_cast<const void*>(kernel));
 }
 static void preload_kernels() {
-  preload(state_reset_kernel); preload(pool_init_kernel); preload(phase_end_kernel); preload(iter_end_kernel); preload(final_topk_kernel);
+  preload(state_reset_kernel); preload(pool_init_kernel); preload(phase_end_kernel); preload(iter_end_kernel); preload(final_topk_kernel); preload(final_push_kernel);
+  preload(bfs_level_kernel); preload(encode_kernel); preload(need_mask_kernel);
   preload(merge_seq_kernel<512, 27, unsigned short>); preload(merge_seq_kernel<1024, 14, unsigned short>);
   preload(merge_seq_kernel<2048, 7, unsigned short>); preload(merge_seq_kernel<4096, 3, unsigned short>);
   preload(merge_seq_kernel<16384, 1, unsigned short>); preload(merge_seq_kernel<0, 4, unsigned int>);
@@ -1797,6 +1872,10 @@ int pprb200_debug_prof(pprb200_session* s, unsigned long long* out, int* n_ctas)
   return PPRB200_OK;
 }
 
+static int peer_push_mode() {
+  const char* e = getenv("PPRB200_PUSH_MODE");
+  return e ? atoi(e) : 0;
+}
 // SM clocks a cross-GPU barrier waits before it declares a peer dead (PPRB200_PEER_TIMEOUT_MS, default 30 s at ~2 GHz)
 static long long peer_timeout_cycles() {
   double ms = 30000.0;
@@ -1880,6 +1959,8 @@ int pprb200_session_ipc_attach(pprb200_session* s, const void* all_handles) {
   pd.world = s->world;
   pd.rank = s->rank;
   pd.timeout_cycles = peer_timeout_cycles();
+  pd.push_mode = peer_push_mode();
+  pd.need = s->d_need;
   for (int r = 0; r < s->world; r++) {
     if (r == s->rank) {
       pd.buf[r][0] = s->d_buf[0]; pd.buf[r][1] = s->d_buf[1]; pd.mbox[r] = s->d_mbox;
@@ -1929,6 +2010,8 @@ int pprb200_session_attach_local(pprb200_session** all, int32_t world) {
     pd.world = world;
     pd.rank = r;
     pd.timeout_cycles = peer_timeout_cycles();
+    pd.push_mode = peer_push_mode();
+    pd.need = all[r]->d_need;
     for (int q = 0; q < world; q++) { pd.buf[q][0] = all[q]->d_buf[0]; pd.buf[q][1] = all[q]->d_buf[1]; pd.mbox[q] = all[q]->d_mbox; }
     cudaSetDevice(all[r]->device);
     preload_kernels();                      // (see preload_kernels: no first-use code load behind a kernel that waits for a peer)
@@ -2190,6 +2273,8 @@ static int run_oneshot(const int64_t* row_ptr, const int32_t* col, int32_t n, co
       pd.world = world;
       pd.rank = r;
       pd.timeout_cycles = peer_timeout_cycles();
+      pd.push_mode = peer_push_mode();
+      pd.need = ss[(size_t)r]->d_need;
       for (int q = 0; q < world; q++) { pd.buf[q][0] = ss[(size_t)q]->d_buf[0]; pd.buf[q][1] = ss[(size_t)q]->d_buf[1]; pd.mbox[q] = ss[(size_t)q]->d_mbox; }
       ss[(size_t)r]->peers = pd;
       ss[(size_t)r]->attached = true;
