@@ -306,7 +306,21 @@ def run_job(w, wname, args, cx, steps, warm, hub_threshold, want_e2e=True, want_
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([dev_ms, merge_ms, walk_ms], dtype=torch.float64, device="cuda")
     stats = sess.stats()
-    pushed = stats["nonsink_node_iterations"] * 12 * ((w["L"] + 3) // 4 * 4) * (world - 1)  # basket bytes this rank stored into its peers (last step)
+    # basket bytes this rank stored into its peers (last step): a basket goes to the ranks that own a predecessor of its node
+    peers_per_basket = float(world - 1)
+    if world > 1 and w["kind"] == "grank":
+        from approximated_personalized_pagerank_b200 import multigpu
+        owner = multigpu.shard_owner(g, colour, hub_threshold, world)
+        src_owner = np.repeat(owner, g.out_degree())
+        need = np.zeros(g.n, dtype=np.int64)
+        for r in range(world):
+            m = np.zeros(g.n, dtype=bool)
+            m[g.col[src_owner == r]] = True
+            need += m & (owner != r)
+        mine = owner == rank
+        peers_per_basket = float(need[mine].mean()) if mine.any() else 0.0
+        del src_owner, need
+    pushed = int(stats["nonsink_node_iterations"] * 12 * ((w["L"] + 3) // 4 * 4) * peers_per_basket)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         # per-rank shards of the job -> whole-job totals (node_iterations is already global: colour sizes x iterations)
@@ -447,7 +461,8 @@ def run_job(w, wname, args, cx, steps, warm, hub_threshold, want_e2e=True, want_
         it_ms = merge_ms / steps / stats["iterations_run"]
         out["nvlink"] = {"bytes_pushed_per_gpu_per_iteration": int(per_it), "achieved": per_it / 1e9 / (it_ms / 1e3) if it_ms > 0 else None,
                          "peak": 900.0, "unit": "GB/s", "frac": per_it / 1e9 / (it_ms / 1e3) / 900.0 if it_ms > 0 else None,
-                         "note": "baskets stored into every peer by the producing CTA (publish_slot), overlapped with the merge; max over ranks"}
+                         "peers_per_basket": peers_per_basket,
+                         "note": "baskets stored by the producing CTA (publish_slot) into the peers that read them (need masks: ranks owning a predecessor), overlapped with the merge; max over ranks; the final completion push is not counted"}
     if world == 1 and want_cpu:
         out["cpu_baseline"] = cpu_baseline(w, g)
     return out

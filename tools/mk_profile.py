@@ -33,7 +33,7 @@ with open(out, "w") as f:
 merge = {k: a for k, a in agg.items() if k.startswith("merge_") or k.startswith("mc_walk")}
 tj = Path("profiles/traffic.json")
 t = json.loads(tj.read_text()) if tj.exists() else {}
-t[workload] = {"command": command, "kernel": "merge_par_kernel + merge_seq_kernel" + (" + mc_walk_kernel" if any(k.startswith("mc_walk") for k in merge) else "") + ", all launches of one run",
+t[workload] = {"command": command, "kernel": "merge_dense_kernel + merge_seq_kernel + merge_par_kernel" + (" + mc_walk_kernel" if any(k.startswith("mc_walk") for k in merge) else "") + ", all launches of one run",
                "dram_bytes_per_step": sum(a[2] for a in merge.values()), "ncu_merge_us": sum(a[1] for a in merge.values()),
                "source": f"{out} (ncu dram__bytes_read.sum + dram__bytes_write.sum)"}
 tj.write_text(json.dumps(t, indent=1))
