@@ -105,6 +105,8 @@ def load():
     lib.pprb200_debug_host_plan.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_uint32, c_int32, c_int32, c_void_p, c_void_p,
                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
     lib.pprb200_shard_owner.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_uint32, c_int32, c_void_p]
+    lib.pprb200_debug_need_mask.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_uint32, c_int32, c_void_p, c_void_p]
+    lib.pprb200_debug_need_mask.restype = c_int
     lib.pprb200_gen_rmat.argtypes = [c_uint32, c_uint32, c_uint64, c_double, c_double, c_double, c_void_p, c_void_p]
     lib.pprb200_gen_ba.argtypes = [c_int32, c_uint32, c_uint64, c_void_p, c_void_p, C.POINTER(c_int64)]
     for name in ("pprb200_find_partitions", "pprb200_find_partitions_device", "pprb200_grank", "pprb200_mccompletepathv2", "pprb200_session_create",

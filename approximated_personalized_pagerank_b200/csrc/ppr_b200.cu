@@ -2162,6 +2162,24 @@ int pprb200_debug_host_plan(const int64_t* row_ptr, const int32_t* col, int32_t 
   return session_create_impl(row_ptr, col, n, colour, 1, hub_threshold, rank, world, nullptr, &unused, true, &o);
 }
 
+// debug / CPU tests: owner and need mask of every node (the plan's per-position arrays mapped back to nodes); host only
+int pprb200_debug_need_mask(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour, uint32_t hub_threshold,
+                            int32_t world, int32_t* owner, uint8_t* need) {
+  if (world < 1 || world > MAX_WORLD) return fail(PPRB200_ERR_PARAM, "world must be 1..%d", MAX_WORLD);
+  int rc = validate_csr(row_ptr, col, n);
+  if (rc) return rc;
+  if (n > 0 && (!owner || !need)) return fail(PPRB200_ERR_PARAM, "NULL argument");
+  std::lock_guard<std::mutex> lk(g_api_mutex);
+  HostPlan H;
+  if ((rc = build_host_plan(row_ptr, col, n, colour, hub_threshold, world, /*need_colour=*/true, H, /*use_device=*/false))) return rc;
+  for (int32_t v = 0; v < n; v++) {
+    const int32_t p = H.pos_of[(size_t)v];
+    owner[v] = p < 0 ? -1 : H.owner_of_pos[(size_t)p];
+    need[v] = (p < 0 || H.need_mask.empty()) ? (uint8_t)0 : H.need_mask[(size_t)p];
+  }
+  return PPRB200_OK;
+}
+
 // which rank of `world` updates node v (-1: sinks, nobody), exactly as the sessions shard the work
 int pprb200_shard_owner(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour_in, uint32_t hub_threshold,
                         int32_t world, int32_t* owner) {

@@ -47,3 +47,15 @@ def connect(sess: Session, dist) -> None:
     dist.all_gather(out, mine)
     attach_handles(sess, torch.stack(out).cpu().numpy())
     dist.barrier()
+
+
+def need_mask(g, colour=None, hub_threshold: int = 0, world: int = 2):
+    """(owner[v], need[v]): the rank that updates node v (-1: sink) and the ranks that read v's basket during the iterations
+    (bit r: rank r owns a predecessor of v) -- where v's owner stores the basket. Host only (pprb200_debug_need_mask)."""
+    lib = _lib.load()
+    owner = np.zeros(max(g.n, 1), dtype=np.int32)
+    need = np.zeros(max(g.n, 1), dtype=np.uint8)
+    col_arr = None if colour is None else np.ascontiguousarray(colour, dtype=np.uint8)
+    _lib.check(lib.pprb200_debug_need_mask(_lib.ptr(g.row_ptr), _lib.ptr(g.col), g.n, _lib.ptr(col_arr), hub_threshold, world,
+                                           _lib.ptr(owner), _lib.ptr(need)))
+    return owner[:g.n], need[:g.n]

@@ -161,10 +161,17 @@ int pprb200_debug_host_plan(const int64_t* row_ptr, const int32_t* col, int32_t 
                             int32_t rank, int32_t world, int32_t* pos_of, int32_t* rank_of, int64_t* row_off, uint32_t* enc,
                             int32_t* item_pos, int64_t* item_off, int32_t* item_len, int32_t item_cap, int32_t* summary);
 
+/* Debug / CPU tests: the multi-GPU push plan of `world` ranks, by NODE (host only). owner[v] = rank that updates v (-1: sink);
+ * need[v] bit r = rank r owns a predecessor of v, i.e. reads v's basket during the iterations -- the ranks v's owner stores
+ * it into (everybody else receives the final basket once, before the top-K). 0 for sinks: they have no basket. */
+int pprb200_debug_need_mask(const int64_t* row_ptr, const int32_t* col, int32_t n, const uint8_t* colour, uint32_t hub_threshold,
+                            int32_t world, int32_t* owner, uint8_t* need);
+
 /* Debug: per-CTA phase cycle counters of the order-free merge kernels (sessions created with PPRB200_PROF=1 in the
  * environment; out[2][8 * sm_count][8], cleared by the call) and merge_dense_kernel's bookkeeping of the last run
- * (out[8]: nodes finished, nodes that ran pass 2, nodes without a lower bound of the cut, hand-overs to merge_par_kernel
- * by reason -- untrusted contribution, too many candidates, tail table full --, split-hub items passed on). */
+ * (out[8]: nodes finished, nodes that ran pass 2, nodes without a lower bound of the cut, successors of the nodes handed to
+ * merge_par_kernel after reading them, nodes selected straight from the tables (candidates > CMAX), tail table full, of those
+ * finished by pass-2 rounds, nodes handed over unread because their old basket was below PPRB200_MIN_OLD entries). */
 int pprb200_debug_prof(pprb200_session* s, unsigned long long* out, int* n_ctas);
 int pprb200_debug_counters(pprb200_session* s, unsigned long long* out);
 /* Debug / known-answer tests: out[i][0..3] = Philox4x32-10 with counter ctr_key[i][0..3] and key ctr_key[i][4..5], computed on the

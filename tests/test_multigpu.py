@@ -26,6 +26,27 @@ def test_shard_plan_covers_every_non_sink_node_once_and_balances_work(world):
         assert work.max() <= max(1.05 * work.mean(), deg[colour == c].max() + 0.05 * work.mean())
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_need_masks_name_exactly_the_ranks_that_read_a_basket(world):
+    """During the iterations a basket is stored only into the ranks that own a predecessor of its node (publish_slot reads
+    PeerDev::need); a mask that misses a reader means stale baskets on that rank, one that names too many wastes NVLink stores.
+    Specification check of the plan on the CPU, by node: R-MAT (hubs read everywhere), BA, a ring (one reader each), sinks."""
+    for g in (G.rmat(11), G.barabasi_albert(3000, 4), G.ring(64), G.from_edges(6, [0, 0, 1, 5], [1, 2, 2, 2])):
+        colour = ppr.find_partitions_csr(g)
+        owner, need = multigpu.need_mask(g, colour, 0, world)
+        assert (owner == multigpu.shard_owner(g, colour, 0, world)).all()
+        deg = g.out_degree()
+        src = np.repeat(np.arange(g.n), deg)
+        want = np.zeros(g.n, dtype=np.int64)
+        np.bitwise_or.at(want, g.col, 1 << owner[src].astype(np.int64))   # every edge v -> u: owner(v) reads u's basket
+        want[deg == 0] = 0                                                 # sinks have no basket to send
+        assert (need.astype(np.int64) == want).all(), int((need != want).sum())
+    # one rank: nothing to send
+    g = G.rmat(9)
+    owner, need = multigpu.need_mask(g, None, 0, 1)
+    assert (need == 0).all() and set(np.unique(owner)) <= {-1, 0}
+
+
 def _gloo_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
