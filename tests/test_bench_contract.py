@@ -44,6 +44,19 @@ def test_default_workload_is_the_configuration_the_target_is_quoted_on():
     assert bench.REFERENCE_SAMPLE_ITERATIONS == 2 and (1 << 22) > bench.REFERENCE_FULL_JOB_NODES
 
 
+def test_committed_ncu_traffic_covers_the_default_workload():
+    """roofline.traffic of the default line comes from the committed ncu launch list (profiles/traffic.json, made by
+    tools/mk_profile.py from profiles/r2/launches_bench_rmat22.csv.gz): the entry must exist, name its source, and stay
+    below the algorithmic bytes of the job (the L2 serves the popular baskets; well above would mean wasted re-reads)"""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    prof = bench.committed_profile(bench.DEFAULT_WORKLOAD)
+    assert prof and prof["dram_bytes_per_step"] > 0 and (ROOT / prof["source"].split(" ")[0]).exists()
+    line = json.loads((ROOT / "profiles" / "r2" / "bench_r2_n1_rmat22.json").read_text().splitlines()[-1])
+    alg = line["roofline"]["algorithmic_bytes_per_step"]
+    assert 0.2 * alg < prof["dram_bytes_per_step"] < 1.5 * alg
+
+
 def test_b200_arm_fails_loudly_without_a_gpu():
     import torch
     if torch.cuda.is_available():
